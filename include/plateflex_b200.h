@@ -1,0 +1,175 @@
+/*
+ * plateflex_b200.h -- C ABI of libplateflex_b200.so
+ *
+ * The drop-in boundary for PlateFlex's data-parallel hot path on B200
+ * (sm_100a).  It replaces the two numpy.f2py extension modules that the
+ * reference builds from Fortran (reference meson.build:46-75):
+ *
+ *     plateflex.cpwt   (src/cpwt/cpwt.f90, src/cpwt/cpwt_sub.f90)
+ *     plateflex.flex   (src/flex/flex.f90)
+ *
+ * plus the per-cell SciPy fit loop of plateflex/estimate.py:227-409 driven by
+ * plateflex/classes.py:1125-1332, which has no native counterpart in the
+ * reference.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns PFX_OK (0) or a PFX_ERR_* code; the message is
+ *     available from pfx_last_error() (thread-local).
+ *   - "_host" entry points take HOST pointers and perform the host<->device
+ *     copies themselves; "_dev" entry points take DEVICE pointers that live on
+ *     the plan's device and enqueue all work on the plan's stream
+ *     (pfx_plan_set_stream) without synchronising.
+ *   - input grids are (nx, ny) float64, C order (y fastest), exactly what
+ *     numpy hands to f2py in classes.py:225.
+ *   - all outputs use the reference's Fortran layout (x fastest):
+ *         maps   (nx, ny, ns)        -> out[ix + nx*(iy + ny*is)]
+ *         cubes  (nx, ny, 11, ns)    -> out[ix + nx*(iy + ny*(ia + 11*is))]
+ *     complex values are interleaved (re, im) float64 pairs.
+ *   - all arithmetic is float64.  The reference is float32 (default-kind REAL,
+ *     cpwt.f90:36,41,72-74); float64 outputs are a superset.
+ */
+#ifndef PLATEFLEX_B200_H
+#define PLATEFLEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFX_NA 11 /* azimuths of the fan wavelet, cpwt.f90:37 */
+
+enum pfx_status {
+    PFX_OK = 0,
+    PFX_ERR_ARG = 1,   /* bad argument (shape, null pointer, range) */
+    PFX_ERR_CUDA = 2,  /* CUDA runtime error */
+    PFX_ERR_CUFFT = 3, /* cuFFT error */
+    PFX_ERR_OOM = 4,   /* device allocation failed */
+    PFX_ERR_STATE = 5  /* call sequence error */
+};
+
+enum pfx_engine {
+    PFX_ENGINE_PRUNED = 0, /* hand-written band-pruned inverse transform (default) */
+    PFX_ENGINE_DENSE = 1   /* daughter multiply + batched cuFFT Z2Z inverse */
+};
+
+enum pfx_atype { /* estimate.py:267,308,349 */
+    PFX_ATYPE_ADMIT = 0,
+    PFX_ATYPE_COH = 1,
+    PFX_ATYPE_JOINT = 2
+};
+
+typedef struct pfx_plan pfx_plan; /* opaque CWT plan: sizes, tables, workspaces */
+
+/* conf_flex module variables (flex.f90:47-48).  rhof is not here: the Fortran
+ * overwrites it from wd on every call (flex.f90:207-211) and so do we.  wd,
+ * and optionally rhoc / zc, are per-cell (classes.py:1087-1091) and passed as
+ * arrays where relevant. */
+typedef struct pfx_flex_conf {
+    double rhoc; /* crustal density   (default 2700, __init__.py:153) */
+    double rhom; /* mantle density    (default 3200) */
+    double rhow; /* water density     (default 1030) */
+    double rhoa; /* air density       (default 0) */
+    double zc;   /* crustal thickness (default 35e3 m) */
+    int32_t boug; /* 1 = Bouguer (A=0), 0 = free air (A=1), flex.f90:200-204 */
+    int32_t pad_;
+} pfx_flex_conf;
+
+/* ---- library ---------------------------------------------------------- */
+int pfx_version(void);
+const char *pfx_last_error(void);
+int pfx_device_count(int *count);
+
+/* cpwt_sub.f90:26-33 (npow2): smallest power of two >= n, at least 2. */
+int pfx_npow2(int n);
+
+/* ---- CWT plan --------------------------------------------------------- */
+/* Fixes (nx, ny, dx, dy, k[ns], k0) -- the arguments of cpwt.wlet_transform
+ * (cpwt.f90:65) other than the data -- allocates device workspaces and builds
+ * the wavenumber / daughter tables (defk cpwt_sub.f90:41-62, wave_function
+ * cpwt_sub.f90:73-99).  dx, dy in km; k in rad/m (kf, cpwt.f90:148); k0 is
+ * conf_cpwt.k0 (cpwt.f90:41).  device = CUDA ordinal. */
+int pfx_plan_create(pfx_plan **plan, int nx, int ny, double dx_km, double dy_km, const double *k_rad_m, int ns,
+                    double k0, int engine, int device);
+int pfx_plan_destroy(pfx_plan *plan);
+/* stream is a cudaStream_t (NULL = legacy default stream). */
+int pfx_plan_set_stream(pfx_plan *plan, void *stream);
+/* padded sizes npow2(2nx), npow2(2ny) (cpwt.f90:94-95) and bytes of device memory held. */
+int pfx_plan_info(const pfx_plan *plan, int *nnx, int *nny, size_t *device_bytes);
+/* number of kernels / library launches this plan has enqueued so far (for bench.py's gpu_launches). */
+int pfx_plan_launch_count(const pfx_plan *plan, long long *kernels);
+/* pruned engine: support half-width of the daughter in units of its k-space sigma (default 9.5). */
+int pfx_plan_set_cutoff(pfx_plan *plan, double nsigma);
+
+/* ---- cpwt.wlet_transform  (cpwt.f90:65-191) --------------------------- */
+/* grid (nx,ny) -> cube (nx,ny,11,ns) complex.  Scales [is0, is1) only; the
+ * output holds is1-is0 scale slabs, the first one being scale is0. */
+int pfx_wlet_transform_host(pfx_plan *plan, const double *grid, int is0, int is1, double *cube);
+int pfx_wlet_transform_dev(pfx_plan *plan, const double *grid_dev, int is0, int is1, double *cube_dev);
+
+/* ---- cpwt.wlet_scalogram  (cpwt.f90:200-241), fused with the transform - */
+int pfx_wlet_scalogram_host(pfx_plan *plan, const double *grid, int is0, int is1, double *wl_sg, double *ewl_sg);
+int pfx_wlet_scalogram_dev(pfx_plan *plan, const double *grid_dev, int is0, int is1, double *wl_sg_dev,
+                           double *ewl_sg_dev);
+
+/* ---- cpwt.wlet_xscalogram (cpwt.f90:250-293), fused -------------------- */
+int pfx_wlet_xscalogram_host(pfx_plan *plan, const double *grid1, const double *grid2, int is0, int is1,
+                             double *wl_xsg /* complex */, double *ewl_xsg);
+int pfx_wlet_xscalogram_dev(pfx_plan *plan, const double *grid1_dev, const double *grid2_dev, int is0, int is1,
+                            double *wl_xsg_dev, double *ewl_xsg_dev);
+
+/* ---- cpwt.wlet_admit_coh  (cpwt.f90:303-364), fused -------------------- */
+/* grid1 = topography, grid2 = gravity (classes.py:966-967). */
+int pfx_wlet_admit_coh_host(pfx_plan *plan, const double *topo, const double *grav, int is0, int is1, double *wl_admit,
+                            double *ewl_admit, double *wl_coh, double *ewl_coh);
+int pfx_wlet_admit_coh_dev(pfx_plan *plan, const double *topo_dev, const double *grav_dev, int is0, int is1,
+                           double *wl_admit_dev, double *ewl_admit_dev, double *wl_coh_dev, double *ewl_coh_dev);
+
+/* ---- cube-input forms: the literal f2py signatures --------------------- */
+/* For callers that already hold wl_trans cubes (classes.py:277, 966).  Host
+ * pointers; streamed through the device one scale slab at a time. */
+int pfx_cube_scalogram_host(int device, int nx, int ny, int ns, const double *wl_trans, double *wl_sg, double *ewl_sg);
+int pfx_cube_xscalogram_host(int device, int nx, int ny, int ns, const double *wl_trans1, const double *wl_trans2,
+                             double *wl_xsg, double *ewl_xsg);
+int pfx_cube_admit_coh_host(int device, int nx, int ny, int ns, const double *wl_trans1, const double *wl_trans2,
+                            double *wl_admit, double *ewl_admit, double *wl_coh, double *ewl_coh);
+
+/* ---- flex.real_xspec_functions (flex.f90:178-235), batched ------------- */
+/* ncurves parameter sets (te[c] km, f[c], alpha[c] rad, wd[c] m) evaluated on
+ * k[ns] (rad/m): admit/coh are [ncurves][ns] row-major.  wd may be NULL (0).
+ * jac_admit / jac_coh (may be NULL) receive the analytic derivatives with
+ * respect to (Te, F, alpha) that the fit uses, as [ncurves][3][ns]. */
+int pfx_flex_xspec_host(int device, const pfx_flex_conf *conf, const double *k, int ns, int ncurves, const double *te,
+                        const double *f, const double *alpha, const double *wd, double *admit, double *coh,
+                        double *jac_admit, double *jac_coh);
+
+/* ---- per-cell L2 fit: estimate.L2_estimate_cell over a grid ------------ */
+/* Replaces the Python loop of Project.estimate_grid (classes.py:1218-1304)
+ * and the SciPy call of estimate.py:274-280 (+5 siblings).
+ *
+ * Inputs are (nx,ny,ns) maps in the layout above; wd is (nx,ny) (x fastest)
+ * and required; rhoc_map / zc_map / mask may be NULL (conf values / no mask;
+ * mask is uint8, non-zero = skip, classes.py:1228-1231).  Cells (i, j) with
+ * i in range(0, nx-nn, nn), j in range(0, ny-nn, nn) are fitted
+ * (classes.py:1218-1219); outputs are (mx, my) = (nx/nn, ny/nn) maps, x
+ * fastest, zero where not fitted (classes.py:1189-1204).  out_alpha /
+ * out_alpha_std may be NULL when alph == 0.  status (int32, may be NULL):
+ * 0 not fitted, 1 converged, 2 iteration limit, 3 bad data (sigma<=0 / NaN:
+ * where SciPy would raise, estimate.py:274 -> ValueError).
+ */
+int pfx_l2_fit_host(int device, const pfx_flex_conf *conf, const double *k, int ns, int nx, int ny,
+                    const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,
+                    const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn,
+                    int alph, int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std,
+                    double *out_alpha, double *out_alpha_std, double *out_chi2, int32_t *status);
+int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const double *k_dev, int ns, int nx, int ny,
+                   const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,
+                   const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn,
+                   int alph, int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std,
+                   double *out_alpha, double *out_alpha_std, double *out_chi2, int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLATEFLEX_B200_H */

@@ -1,0 +1,156 @@
+"""Stand-in for the f2py extension module ``plateflex.cpwt`` (built by the
+reference from src/cpwt/cpwt.f90 + cpwt_sub.f90, meson.build:60-75).
+
+``from plateflex_b200.cpwt import cpwt, conf_cpwt`` gives two objects with the
+attribute names f2py generates (lower-case): the four drivers on ``cpwt`` and
+the module variables ``k0`` / ``na`` / ``pi`` on ``conf_cpwt``.  Every call goes
+through the C ABI of libplateflex_b200.so and runs on the GPU.
+
+Differences from the f2py module, all documented in DESIGN.md:
+  * arithmetic and outputs are float64 / complex128 (the Fortran is float32);
+  * inputs are not truncated to float32;
+  * no progress text is written to stdout (cpwt.f90:142,152,189,360).
+Output arrays are Fortran-ordered exactly like f2py's ``intent(out)`` arrays.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["cpwt", "conf_cpwt", "fused"]
+
+
+class _ConfCpwt:
+    """conf_cpwt (cpwt.f90:32-43).  ``k0`` is a float32 Fortran variable: a value written
+    from Python is rounded to float32 and reads back as such (5.336 -> 5.335999965667725),
+    which is what classes._lam2k sees (classes.py:1811)."""
+
+    pi = float(np.float32(3.141592653589793))  # REAL, PARAMETER (cpwt.f90:36)
+    na = _lib.NA  # cpwt.f90:37
+
+    def __init__(self):
+        self._k0 = np.float32(0.0)
+
+    @property
+    def k0(self):
+        return float(self._k0)
+
+    @k0.setter
+    def k0(self, value):
+        self._k0 = np.float32(value)
+
+
+conf_cpwt = _ConfCpwt()
+
+
+def _grid(a, name):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be a 2-D array, got shape {a.shape}")  # f2py: rank mismatch
+    return a
+
+
+def _cube(a, name):
+    a = np.asarray(a)
+    if a.ndim != 4 or a.shape[2] != _lib.NA:
+        raise ValueError(f"{name} must have shape (nx, ny, {_lib.NA}, ns), got {a.shape}")
+    return np.asfortranarray(a, dtype=np.complex128)
+
+
+def _maps(nx, ny, ns, n, dtype=np.float64):
+    return [np.empty((nx, ny, ns), dtype=dtype, order="F") for _ in range(n)]
+
+
+class _Cpwt:
+    """The ``cpwt`` Fortran module (cpwt.f90:54-366) as seen through f2py."""
+
+    def wlet_transform(self, grid, dx, dy, kf):
+        """cpwt.f90:65-191.  grid (nx,ny), dx, dy [km], kf (ns) [rad/m] -> complex (nx,ny,11,ns)."""
+        g = _grid(grid, "grid")
+        kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
+        nx, ny = g.shape
+        plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
+        out = np.empty((nx, ny, _lib.NA, len(kf)), dtype=np.complex128, order="F")
+        _lib.check(_lib.lib.pfx_wlet_transform_host(plan.handle, _lib.ptr(g), 0, len(kf), _lib.ptr(out)))
+        return out
+
+    def wlet_scalogram(self, wl_trans):
+        """cpwt.f90:200-241.  complex (nx,ny,11,ns) -> (wl_sg, ewl_sg), each (nx,ny,ns)."""
+        w = _cube(wl_trans, "wl_trans")
+        nx, ny, _, ns = w.shape
+        sg, esg = _maps(nx, ny, ns, 2)
+        _lib.check(_lib.lib.pfx_cube_scalogram_host(_lib.default_device(), nx, ny, ns, _lib.ptr(w), _lib.ptr(sg),
+                                                    _lib.ptr(esg)))
+        return sg, esg
+
+    def wlet_xscalogram(self, wl_trans1, wl_trans2):
+        """cpwt.f90:250-293.  -> (wl_xsg complex (nx,ny,ns), ewl_xsg (nx,ny,ns))."""
+        w1, w2 = _cube(wl_trans1, "wl_trans1"), _cube(wl_trans2, "wl_trans2")
+        if w1.shape != w2.shape:
+            raise ValueError("wl_trans1 and wl_trans2 must have the same shape")
+        nx, ny, _, ns = w1.shape
+        xsg = np.empty((nx, ny, ns), dtype=np.complex128, order="F")
+        (exsg,) = _maps(nx, ny, ns, 1)
+        _lib.check(_lib.lib.pfx_cube_xscalogram_host(_lib.default_device(), nx, ny, ns, _lib.ptr(w1), _lib.ptr(w2),
+                                                     _lib.ptr(xsg), _lib.ptr(exsg)))
+        return xsg, exsg
+
+    def wlet_admit_coh(self, wl_trans1, wl_trans2):
+        """cpwt.f90:303-364.  -> (wl_admit, ewl_admit, wl_coh, ewl_coh), each (nx,ny,ns)."""
+        w1, w2 = _cube(wl_trans1, "wl_trans1"), _cube(wl_trans2, "wl_trans2")
+        if w1.shape != w2.shape:
+            raise ValueError("wl_trans1 and wl_trans2 must have the same shape")
+        nx, ny, _, ns = w1.shape
+        outs = _maps(nx, ny, ns, 4)
+        _lib.check(_lib.lib.pfx_cube_admit_coh_host(_lib.default_device(), nx, ny, ns, _lib.ptr(w1), _lib.ptr(w2),
+                                                    *[_lib.ptr(o) for o in outs]))
+        return tuple(outs)
+
+
+cpwt = _Cpwt()
+
+
+class _Fused:
+    """Grid-in forms that never materialise the (nx,ny,11,ns) cube: what Grid.wlet_scalogram and
+    Project.wlet_admit_coh use when no ``wl_trans`` attribute exists (classes.py:276-280, 950-967)."""
+
+    def wlet_scalogram(self, grid, dx, dy, kf, scales=None):
+        g = _grid(grid, "grid")
+        kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
+        nx, ny = g.shape
+        is0, is1 = scales if scales is not None else (0, len(kf))
+        plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
+        sg, esg = _maps(nx, ny, is1 - is0, 2)
+        _lib.check(_lib.lib.pfx_wlet_scalogram_host(plan.handle, _lib.ptr(g), is0, is1, _lib.ptr(sg), _lib.ptr(esg)))
+        return sg, esg
+
+    def wlet_xscalogram(self, grid1, grid2, dx, dy, kf, scales=None):
+        g1, g2 = _grid(grid1, "grid1"), _grid(grid2, "grid2")
+        if g1.shape != g2.shape:
+            raise ValueError("grids must have the same shape")
+        kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
+        nx, ny = g1.shape
+        is0, is1 = scales if scales is not None else (0, len(kf))
+        plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
+        xsg = np.empty((nx, ny, is1 - is0), dtype=np.complex128, order="F")
+        (exsg,) = _maps(nx, ny, is1 - is0, 1)
+        _lib.check(_lib.lib.pfx_wlet_xscalogram_host(plan.handle, _lib.ptr(g1), _lib.ptr(g2), is0, is1, _lib.ptr(xsg),
+                                                     _lib.ptr(exsg)))
+        return xsg, exsg
+
+    def wlet_admit_coh(self, topo, grav, dx, dy, kf, scales=None, out=None):
+        g1, g2 = _grid(topo, "topo"), _grid(grav, "grav")
+        if g1.shape != g2.shape:
+            raise ValueError("grids must have the same shape")
+        kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
+        nx, ny = g1.shape
+        is0, is1 = scales if scales is not None else (0, len(kf))
+        plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
+        outs = out if out is not None else _maps(nx, ny, is1 - is0, 4)
+        _lib.check(_lib.lib.pfx_wlet_admit_coh_host(plan.handle, _lib.ptr(g1), _lib.ptr(g2), is0, is1,
+                                                    *[_lib.ptr(o) for o in outs]))
+        return tuple(outs)
+
+
+fused = _Fused()

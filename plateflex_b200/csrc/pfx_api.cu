@@ -1,0 +1,492 @@
+// pfx_api.cu -- C ABI of libplateflex_b200.so: plan management and the CWT entry
+// points declared in include/plateflex_b200.h.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+
+#include "pfx_plan.hpp"
+
+namespace pfx {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int plan_init_axes(pfx_plan *pl);
+int plan_init_pruned(pfx_plan *pl);
+int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);
+PlaneView pruned_view(const pfx_plan *pl, int g);
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace pfx
+
+using namespace pfx;
+
+int pfx_plan::alloc(void **p, size_t bytes)
+{
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return PFX_ERR_OOM;
+    }
+    owned.push_back(*p);
+    device_bytes += bytes;
+    return PFX_OK;
+}
+
+int pfx_plan::scratch(int slot, size_t bytes, void **p)
+{
+    if (bytes > scratch_bytes[slot]) {
+        if (d_scratch[slot]) {
+            PFX_CUDA(cudaStreamSynchronize(stream));
+            PFX_CUDA(cudaFree(d_scratch[slot]));
+            device_bytes -= scratch_bytes[slot];
+            d_scratch[slot] = nullptr;
+            scratch_bytes[slot] = 0;
+        }
+        cudaError_t e = cudaMalloc(&d_scratch[slot], bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return PFX_ERR_OOM;
+        }
+        scratch_bytes[slot] = bytes;
+        device_bytes += bytes;
+    }
+    *p = d_scratch[slot];
+    return PFX_OK;
+}
+
+extern "C" {
+
+int pfx_version(void) { return 100; }
+
+const char *pfx_last_error(void) { return g_err.c_str(); }
+
+int pfx_device_count(int *count)
+{
+    PFX_ARG(count, "count is null");
+    PFX_CUDA(cudaGetDeviceCount(count));
+    return PFX_OK;
+}
+
+int pfx_npow2(int n)
+{
+    int n2 = 1;
+    do n2 *= 2;
+    while (n2 < n);
+    return n2;
+}
+
+int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, const double *k_rad_m, int ns, double k0,
+                    int engine, int device)
+{
+    PFX_ARG(out, "plan is null");
+    *out = nullptr;
+    PFX_ARG(nx >= 2 && ny >= 2 && nx <= (1 << 14) && ny <= (1 << 14), "nx, ny must be in [2, 16384]");
+    PFX_ARG(dx_km > 0 && dy_km > 0, "dx, dy must be positive");
+    PFX_ARG(k_rad_m && ns >= 1, "k is null or ns < 1");
+    PFX_ARG(k0 > 0, "k0 must be positive");
+    PFX_ARG(engine == PFX_ENGINE_PRUNED || engine == PFX_ENGINE_DENSE, "unknown engine");
+    for (int i = 0; i < ns; i++) PFX_ARG(k_rad_m[i] > 0 && std::isfinite(k_rad_m[i]), "k must be positive and finite");
+    int ndev = 0;
+    PFX_CUDA(cudaGetDeviceCount(&ndev));
+    PFX_ARG(device >= 0 && device < ndev, "device ordinal out of range");
+    DeviceGuard guard(device);
+
+    pfx_plan *pl = new pfx_plan();
+    pl->nx = nx;
+    pl->ny = ny;
+    pl->ns = ns;
+    pl->NX = pfx_npow2(2 * nx);  // cpwt.f90:94-95
+    pl->NY = pfx_npow2(2 * ny);
+    pl->dx = dx_km;
+    pl->dy = dy_km;
+    pl->k0 = k0;
+    pl->engine = engine;
+    pl->device = device;
+    pl->k.assign(k_rad_m, k_rad_m + ns);
+
+    // Scale / angle constants (cpwt.f90:131,148-161; cpwt_sub.f90:85-87).
+    const double pi = 3.141592653589793;
+    const double da = 2. * std::sqrt(-2. * std::log(0.75)) / k0;
+    pl->consts.resize(ns);
+    for (int is = 0; is < ns; is++) {
+        PfxScaleConsts &c = pl->consts[is];
+        const double kk = pl->k[is] * 1.e3;
+        c.s = k0 / kk;
+        c.norm = c.s / std::sqrt(pi);
+        for (int ia = 0; ia < PFX_NA; ia++) {
+            const double angle = (double)ia * da - pi / 2.e0;
+            c.kx0[ia] = k0 * std::cos(angle);
+            c.ky0[ia] = k0 * std::sin(angle);
+            c.e0[ia] = std::exp(-0.5 * (c.kx0[ia] * c.kx0[ia] + c.ky0[ia] * c.ky0[ia]));
+        }
+    }
+
+    auto fail = [&](int rc) {
+        pfx_plan_destroy(pl);
+        return rc;
+    };
+    const size_t P = (size_t)pl->NX * pl->NY;
+    int rc;
+    if ((rc = pl->alloc((void **)&pl->d_kx, pl->NX * sizeof(double)))) return fail(rc);
+    if ((rc = pl->alloc((void **)&pl->d_ky, pl->NY * sizeof(double)))) return fail(rc);
+    if ((rc = pl->alloc((void **)&pl->d_u2, pl->NX * sizeof(double)))) return fail(rc);
+    if ((rc = pl->alloc((void **)&pl->d_v2, pl->NY * sizeof(double)))) return fail(rc);
+    if ((rc = pl->alloc((void **)&pl->d_partial, 512 * sizeof(double)))) return fail(rc);
+    for (int g = 0; g < 2; g++)
+        if ((rc = pl->alloc((void **)&pl->d_spec[g], P * sizeof(double2)))) return fail(rc);
+    if ((rc = plan_init_axes(pl))) return fail(rc);
+
+    // forward FFT plan (cpwt.f90:122): one 2-D Z2Z per grid, work area owned by the plan
+    {
+        size_t ws = 0;
+        cufftResult r = cufftCreate(&pl->fft_fwd);
+        if (r == CUFFT_SUCCESS) {
+            pl->fft_fwd_ok = true;
+            r = cufftSetAutoAllocation(pl->fft_fwd, 0);
+        }
+        int n[2] = {pl->NY, pl->NX};
+        if (r == CUFFT_SUCCESS) r = cufftMakePlanMany(pl->fft_fwd, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2Z, 1, &ws);
+        if (r != CUFFT_SUCCESS) {
+            set_error("cufft forward plan %dx%d failed: %d", pl->NY, pl->NX, (int)r);
+            return fail(PFX_ERR_CUFFT);
+        }
+        if ((rc = pl->alloc(&pl->d_fft_work, ws))) return fail(rc);
+        pl->fft_work_bytes = ws;
+        if (cufftSetWorkArea(pl->fft_fwd, pl->d_fft_work) != CUFFT_SUCCESS) return fail(PFX_ERR_CUFFT);
+    }
+    rc = (engine == PFX_ENGINE_DENSE) ? plan_init_dense(pl) : plan_init_pruned(pl);
+    if (rc) return fail(rc);
+    cudaError_t e = cudaStreamSynchronize(pl->stream);
+    if (e != cudaSuccess) {
+        set_error("plan initialisation failed: %s", cudaGetErrorString(e));
+        return fail(PFX_ERR_CUDA);
+    }
+    *out = pl;
+    return PFX_OK;
+}
+
+int pfx_plan_destroy(pfx_plan *pl)
+{
+    if (!pl) return PFX_OK;
+    DeviceGuard guard(pl->device);
+    cudaDeviceSynchronize();
+    if (pl->fft_fwd_ok) cufftDestroy(pl->fft_fwd);
+    for (int g = 0; g < 2; g++)
+        if (pl->fft_inv_ok[g]) cufftDestroy(pl->fft_inv[g]);
+    for (void *p : pl->owned) cudaFree(p);
+    for (void *p : pl->d_scratch)
+        if (p) cudaFree(p);
+    delete pl;
+    return PFX_OK;
+}
+
+int pfx_plan_set_stream(pfx_plan *pl, void *stream)
+{
+    PFX_ARG(pl, "plan is null");
+    pl->stream = (cudaStream_t)stream;
+    return PFX_OK;
+}
+
+int pfx_plan_info(const pfx_plan *pl, int *nnx, int *nny, size_t *device_bytes)
+{
+    PFX_ARG(pl, "plan is null");
+    if (nnx) *nnx = pl->NX;
+    if (nny) *nny = pl->NY;
+    if (device_bytes) *device_bytes = pl->device_bytes;
+    return PFX_OK;
+}
+
+int pfx_plan_launch_count(const pfx_plan *pl, long long *kernels)
+{
+    PFX_ARG(pl && kernels, "null argument");
+    *kernels = pl->launches;
+    return PFX_OK;
+}
+
+int pfx_plan_set_cutoff(pfx_plan *pl, double nsigma)
+{
+    PFX_ARG(pl, "plan is null");
+    PFX_ARG(nsigma >= 4.0, "cutoff must be >= 4 sigma");
+    pl->cutoff = nsigma;
+    if (pl->engine == PFX_ENGINE_PRUNED) {
+        DeviceGuard guard(pl->device);
+        return plan_init_pruned(pl);
+    }
+    return PFX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// Shared driver: forward spectra once (cpwt.f90:122), then per scale the 11 azimuth
+// planes of each grid followed by the requested epilogue.
+// ------------------------------------------------------------------------------------
+namespace {
+
+enum { OUT_CUBE = 100 };
+
+int check_range(const pfx_plan *pl, int is0, int is1)
+{
+    PFX_ARG(pl, "plan is null");
+    PFX_ARG(is0 >= 0 && is1 <= pl->ns && is0 < is1, "scale range [is0, is1) out of bounds");
+    return PFX_OK;
+}
+
+int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *o0, double *o1,
+            double *o2, double *o3)
+{
+    const int ngrids = g2 ? 2 : 1;
+    const size_t nxy = (size_t)pl->nx * pl->ny;
+    PFX_CHECK(forward_spectrum(pl, g1, 0));
+    if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
+    for (int is = is0; is < is1; is++) {
+        const size_t so = (size_t)(is - is0) * nxy;
+        PlaneView v1, v2;
+        if (pl->engine == PFX_ENGINE_DENSE) {
+            PFX_CHECK(dense_scale_planes(pl, is, ngrids));
+            v1 = dense_view(pl, 0);
+            v2 = dense_view(pl, ngrids - 1);
+        } else {
+            PFX_CHECK(pruned_scale_planes(pl, is, ngrids));
+            v1 = pruned_view(pl, 0);
+            v2 = pruned_view(pl, ngrids - 1);
+        }
+        if (mode == OUT_CUBE) {
+            PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(o0) + so * PFX_NA, pl->stream));
+        } else if (mode == RED_XSCALOGRAM) {
+            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o0 + 2 * so, o1 + so, nullptr, nullptr, pl->stream));
+        } else {
+            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o0 + so, o1 + so, o2 ? o2 + so : nullptr,
+                                    o3 ? o3 + so : nullptr, pl->stream));
+        }
+        pl->launches++;
+    }
+    return PFX_OK;
+}
+
+// Host wrapper: stage the inputs, run, copy the outputs back, synchronise.
+// outs[i] has out_elems[i] doubles per scale.
+int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *outs,
+                 const int *out_elems_per_cell, int nouts)
+{
+    DeviceGuard guard(pl->device);
+    const size_t nxy = (size_t)pl->nx * pl->ny;
+    const int nsc = is1 - is0;
+    double *d_g[2] = {nullptr, nullptr};
+    PFX_CHECK(pl->scratch(0, nxy * sizeof(double), (void **)&d_g[0]));
+    PFX_CUDA(cudaMemcpyAsync(d_g[0], g1, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    if (g2) {
+        PFX_CHECK(pl->scratch(1, nxy * sizeof(double), (void **)&d_g[1]));
+        PFX_CUDA(cudaMemcpyAsync(d_g[1], g2, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    }
+    double *d_o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < nouts; i++)
+        PFX_CHECK(pl->scratch(2 + i, nxy * nsc * out_elems_per_cell[i] * sizeof(double), (void **)&d_o[i]));
+    PFX_CHECK(run_cwt(pl, mode, d_g[0], d_g[1], is0, is1, d_o[0], d_o[1], d_o[2], d_o[3]));
+    for (int i = 0; i < nouts; i++)
+        PFX_CUDA(cudaMemcpyAsync(outs[i], d_o[i], nxy * nsc * out_elems_per_cell[i] * sizeof(double),
+                                 cudaMemcpyDeviceToHost, pl->stream));
+    PFX_CUDA(cudaStreamSynchronize(pl->stream));
+    return PFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pfx_wlet_transform_dev(pfx_plan *pl, const double *grid, int is0, int is1, double *cube)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && cube, "null pointer");
+    DeviceGuard guard(pl->device);
+    return run_cwt(pl, OUT_CUBE, grid, nullptr, is0, is1, cube, nullptr, nullptr, nullptr);
+}
+
+int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, double *cube)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && cube, "null pointer");
+    // One scale slab (nx*ny*11 complex) at a time: the whole cube need not fit on the device.
+    DeviceGuard guard(pl->device);
+    const size_t nxy = (size_t)pl->nx * pl->ny, slab = nxy * PFX_NA * 2;
+    double *d_g = nullptr, *d_slab = nullptr;
+    PFX_CHECK(pl->scratch(0, nxy * sizeof(double), (void **)&d_g));
+    PFX_CHECK(pl->scratch(2, slab * sizeof(double), (void **)&d_slab));
+    PFX_CUDA(cudaMemcpyAsync(d_g, grid, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    PFX_CHECK(forward_spectrum(pl, d_g, 0));
+    for (int is = is0; is < is1; is++) {
+        PlaneView v;
+        if (pl->engine == PFX_ENGINE_DENSE) {
+            PFX_CHECK(dense_scale_planes(pl, is, 1));
+            v = dense_view(pl, 0);
+        } else {
+            PFX_CHECK(pruned_scale_planes(pl, is, 1));
+            v = pruned_view(pl, 0);
+        }
+        PFX_CHECK(launch_crop(pl->nx, pl->ny, v, reinterpret_cast<double2 *>(d_slab), pl->stream));
+        pl->launches++;
+        PFX_CUDA(cudaMemcpyAsync(cube + (size_t)(is - is0) * slab, d_slab, slab * sizeof(double), cudaMemcpyDeviceToHost,
+                                 pl->stream));
+        PFX_CUDA(cudaStreamSynchronize(pl->stream));
+    }
+    return PFX_OK;
+}
+
+int pfx_wlet_scalogram_dev(pfx_plan *pl, const double *grid, int is0, int is1, double *wl_sg, double *ewl_sg)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && wl_sg && ewl_sg, "null pointer");
+    DeviceGuard guard(pl->device);
+    return run_cwt(pl, RED_SCALOGRAM, grid, nullptr, is0, is1, wl_sg, ewl_sg, nullptr, nullptr);
+}
+
+int pfx_wlet_scalogram_host(pfx_plan *pl, const double *grid, int is0, int is1, double *wl_sg, double *ewl_sg)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && wl_sg && ewl_sg, "null pointer");
+    double *outs[2] = {wl_sg, ewl_sg};
+    const int el[2] = {1, 1};
+    return run_cwt_host(pl, RED_SCALOGRAM, grid, nullptr, is0, is1, outs, el, 2);
+}
+
+int pfx_wlet_xscalogram_dev(pfx_plan *pl, const double *g1, const double *g2, int is0, int is1, double *wl_xsg,
+                            double *ewl_xsg)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(g1 && g2 && wl_xsg && ewl_xsg, "null pointer");
+    DeviceGuard guard(pl->device);
+    return run_cwt(pl, RED_XSCALOGRAM, g1, g2, is0, is1, wl_xsg, ewl_xsg, nullptr, nullptr);
+}
+
+int pfx_wlet_xscalogram_host(pfx_plan *pl, const double *g1, const double *g2, int is0, int is1, double *wl_xsg,
+                             double *ewl_xsg)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(g1 && g2 && wl_xsg && ewl_xsg, "null pointer");
+    double *outs[2] = {wl_xsg, ewl_xsg};
+    const int el[2] = {2, 1};
+    return run_cwt_host(pl, RED_XSCALOGRAM, g1, g2, is0, is1, outs, el, 2);
+}
+
+int pfx_wlet_admit_coh_dev(pfx_plan *pl, const double *topo, const double *grav, int is0, int is1, double *wl_admit,
+                           double *ewl_admit, double *wl_coh, double *ewl_coh)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(topo && grav && wl_admit && ewl_admit && wl_coh && ewl_coh, "null pointer");
+    DeviceGuard guard(pl->device);
+    return run_cwt(pl, RED_ADMIT_COH, topo, grav, is0, is1, wl_admit, ewl_admit, wl_coh, ewl_coh);
+}
+
+int pfx_wlet_admit_coh_host(pfx_plan *pl, const double *topo, const double *grav, int is0, int is1, double *wl_admit,
+                            double *ewl_admit, double *wl_coh, double *ewl_coh)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(topo && grav && wl_admit && ewl_admit && wl_coh && ewl_coh, "null pointer");
+    double *outs[4] = {wl_admit, ewl_admit, wl_coh, ewl_coh};
+    const int el[4] = {1, 1, 1, 1};
+    return run_cwt_host(pl, RED_ADMIT_COH, topo, grav, is0, is1, outs, el, 4);
+}
+
+// ---- cube-input forms -----------------------------------------------------------------
+static int cube_reduce_host(int device, int mode, int nx, int ny, int ns, const double *w1, const double *w2, double *o0,
+                            double *o1, double *o2, double *o3)
+{
+    PFX_ARG(nx >= 1 && ny >= 1 && ns >= 1, "bad cube shape");
+    int ndev = 0;
+    PFX_CUDA(cudaGetDeviceCount(&ndev));
+    PFX_ARG(device >= 0 && device < ndev, "device ordinal out of range");
+    DeviceGuard guard(device);
+    const size_t nxy = (size_t)nx * ny, slab = nxy * PFX_NA;
+    double2 *d_w[2] = {nullptr, nullptr};
+    double *d_o[4] = {nullptr, nullptr, nullptr, nullptr};
+    const int e0 = (mode == RED_XSCALOGRAM) ? 2 : 1;
+    int rc = PFX_OK;
+    auto cleanup = [&]() {
+        for (auto p : d_w) cudaFree(p);
+        for (auto p : d_o) cudaFree(p);
+    };
+#define CUBE_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+            cleanup();                                                                       \
+            return e_ == cudaErrorMemoryAllocation ? PFX_ERR_OOM : PFX_ERR_CUDA;             \
+        }                                                                                    \
+    } while (0)
+    CUBE_CUDA(cudaMalloc(&d_w[0], slab * sizeof(double2)));
+    if (w2) CUBE_CUDA(cudaMalloc(&d_w[1], slab * sizeof(double2)));
+    CUBE_CUDA(cudaMalloc(&d_o[0], nxy * e0 * sizeof(double)));
+    CUBE_CUDA(cudaMalloc(&d_o[1], nxy * sizeof(double)));
+    if (mode == RED_ADMIT_COH) {
+        CUBE_CUDA(cudaMalloc(&d_o[2], nxy * sizeof(double)));
+        CUBE_CUDA(cudaMalloc(&d_o[3], nxy * sizeof(double)));
+    }
+    for (int is = 0; is < ns && rc == PFX_OK; is++) {
+        CUBE_CUDA(cudaMemcpyAsync(d_w[0], w1 + 2 * slab * is, slab * sizeof(double2), cudaMemcpyHostToDevice, 0));
+        if (w2) CUBE_CUDA(cudaMemcpyAsync(d_w[1], w2 + 2 * slab * is, slab * sizeof(double2), cudaMemcpyHostToDevice, 0));
+        PlaneView v1{d_w[0], nxy, nx, 0, 0, 1.0}, v2{w2 ? d_w[1] : d_w[0], nxy, nx, 0, 0, 1.0};
+        rc = launch_reduce(mode, nx, ny, v1, v2, d_o[0], d_o[1], d_o[2], d_o[3], 0);
+        if (rc != PFX_OK) break;
+        CUBE_CUDA(cudaMemcpyAsync(o0 + nxy * e0 * is, d_o[0], nxy * e0 * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        CUBE_CUDA(cudaMemcpyAsync(o1 + nxy * is, d_o[1], nxy * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        if (mode == RED_ADMIT_COH) {
+            CUBE_CUDA(cudaMemcpyAsync(o2 + nxy * is, d_o[2], nxy * sizeof(double), cudaMemcpyDeviceToHost, 0));
+            CUBE_CUDA(cudaMemcpyAsync(o3 + nxy * is, d_o[3], nxy * sizeof(double), cudaMemcpyDeviceToHost, 0));
+        }
+        CUBE_CUDA(cudaStreamSynchronize(0));
+    }
+#undef CUBE_CUDA
+    cleanup();
+    return rc;
+}
+
+int pfx_cube_scalogram_host(int device, int nx, int ny, int ns, const double *wl_trans, double *wl_sg, double *ewl_sg)
+{
+    PFX_ARG(wl_trans && wl_sg && ewl_sg, "null pointer");
+    return cube_reduce_host(device, RED_SCALOGRAM, nx, ny, ns, wl_trans, nullptr, wl_sg, ewl_sg, nullptr, nullptr);
+}
+
+int pfx_cube_xscalogram_host(int device, int nx, int ny, int ns, const double *w1, const double *w2, double *wl_xsg,
+                             double *ewl_xsg)
+{
+    PFX_ARG(w1 && w2 && wl_xsg && ewl_xsg, "null pointer");
+    return cube_reduce_host(device, RED_XSCALOGRAM, nx, ny, ns, w1, w2, wl_xsg, ewl_xsg, nullptr, nullptr);
+}
+
+int pfx_cube_admit_coh_host(int device, int nx, int ny, int ns, const double *w1, const double *w2, double *wl_admit,
+                            double *ewl_admit, double *wl_coh, double *ewl_coh)
+{
+    PFX_ARG(w1 && w2 && wl_admit && ewl_admit && wl_coh && ewl_coh, "null pointer");
+    return cube_reduce_host(device, RED_ADMIT_COH, nx, ny, ns, w1, w2, wl_admit, ewl_admit, wl_coh, ewl_coh);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// pfx_common.cuh -- shared declarations of libplateflex_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "plateflex_b200.h"
+
+namespace pfx {
+
+void set_error(const char *fmt, ...);
+
+#define PFX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            pfx::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+            return e_ == cudaErrorMemoryAllocation ? PFX_ERR_OOM : PFX_ERR_CUDA;                    \
+        }                                                                                           \
+    } while (0)
+
+#define PFX_CUFFT(call)                                                                             \
+    do {                                                                                            \
+        cufftResult r_ = (call);                                                                    \
+        if (r_ != CUFFT_SUCCESS) {                                                                  \
+            pfx::set_error("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #call, (int)r_);        \
+            return r_ == CUFFT_ALLOC_FAILED ? PFX_ERR_OOM : PFX_ERR_CUFFT;                          \
+        }                                                                                           \
+    } while (0)
+
+#define PFX_CHECK(expr)                 \
+    do {                                \
+        int rc_ = (expr);               \
+        if (rc_ != PFX_OK) return rc_;  \
+    } while (0)
+
+#define PFX_ARG(cond, msg)                                    \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            pfx::set_error("invalid argument: %s", msg);      \
+            return PFX_ERR_ARG;                               \
+        }                                                     \
+    } while (0)
+
+// A set of complex wavelet-coefficient planes W[p](i, j) as the reduction
+// kernels see them: value = scale * base[p*plane_stride + (j+off_j)*ld + (i+off_i)].
+// The dense engine hands over whole padded cuFFT planes (off = +1: the one-sample
+// shift of cpwt.f90:173-185, scale = 1/(nnx*nny) of cpwt.f90:177); the pruned engine
+// and the cube-input forms hand over compact (nx, ny) planes.
+struct PlaneView {
+    const double2 *base;
+    size_t plane_stride;
+    int ld;
+    int off_i, off_j;
+    double scale;
+};
+
+enum ReduceMode { RED_SCALOGRAM = 0, RED_XSCALOGRAM = 1, RED_ADMIT_COH = 2 };
+
+// K3: azimuth reduction + running-prefix jackknife for one scale.
+//   RED_SCALOGRAM : w1 -> out0 = wl_sg, out1 = ewl_sg                       (cpwt.f90:200-241)
+//   RED_XSCALOGRAM: w1,w2 -> out0 = wl_xsg (complex), out1 = ewl_xsg        (cpwt.f90:250-293)
+//   RED_ADMIT_COH : w1,w2 -> out0..3 = wl_admit, ewl_admit, wl_coh, ewl_coh (cpwt.f90:303-364)
+// Each out* points at the (nx, ny) plane of this scale (x fastest).
+int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
+                  double *out3, cudaStream_t stream);
+
+// K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab.
+int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream);
+
+}  // namespace pfx

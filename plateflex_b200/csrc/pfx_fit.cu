@@ -1,0 +1,904 @@
+// pfx_fit.cu -- K5/K6: batched flexural-model evaluation and the per-cell
+// bounded non-linear least-squares fit of (Te, F[, alpha]).
+//
+// Replaces, for a whole grid in one launch,
+//   Project.estimate_grid / estimate_cell   classes.py:1031-1123, 1218-1304
+//   estimate.L2_estimate_cell               estimate.py:227-409
+//   scipy.optimize.curve_fit(bounds=...)    -> least_squares(method='trf')
+// The reference's optimiser is SciPy's Trust-Region-Reflective method (bounded
+// problem, exact trust-region solver, x_scale=1, ftol=xtol=gtol=1e-8,
+// max_nfev=1000), an un-vendored dependency; its published algorithm
+// (Branch, Coleman & Li 1999; More 1977 for the trust-region sub-problem) is
+// restated here for n<=3 parameters.  With n<=3 everything the method needs
+// from the Jacobian is the n x n matrix J^T J and the gradient J^T f, which a
+// group of G lanes accumulates over the wavelet-scale axis with shuffles; the
+// SVD of the (augmented, Coleman-Li scaled) Jacobian becomes a Jacobi
+// eigen-decomposition of an n x n matrix.  The Jacobian is analytic
+// (pfx_flex.cuh) where SciPy uses 2-point finite differences.
+//
+// One group of G lanes per grid cell, scales strided over the lanes; all lanes
+// of a group carry identical copies of the small dense algebra.
+#include <cfloat>
+
+#include "pfx_flex.cuh"
+
+namespace pfx {
+
+namespace {
+
+constexpr double TRF_FTOL = 1e-8, TRF_XTOL = 1e-8, TRF_GTOL = 1e-8;  // least_squares defaults
+constexpr int TRF_MAX_NFEV = 1000;                                    // estimate.py:279
+constexpr double DBL_EPS = 2.220446049250313e-16;
+
+struct FitArgs {
+    pfx_flex_conf conf;
+    const double *k;
+    int ns, nx, ny;
+    const double *adm, *eadm, *coh, *ecoh;
+    const double *wd, *rhoc_map, *zc_map;
+    const uint8_t *mask;
+    int nn, atype;
+    int fx, fy;  // number of fitted cells along x, y: len(range(0, nx-nn, nn))
+    int mx, my;  // output map shape (nx/nn, ny/nn)
+    double *o_te, *o_te_std, *o_f, *o_f_std, *o_a, *o_a_std, *o_chi2;
+    int32_t *status;
+};
+
+template <int NP>
+struct Normal {  // 0.5*sum r^2, J^T r, J^T J
+    double cost;
+    double g[NP];
+    double B[NP][NP];
+};
+
+template <int NP>
+__device__ __forceinline__ double vnorm(const double (&a)[NP])
+{
+    double s = 0.;
+#pragma unroll
+    for (int i = 0; i < NP; i++) s += a[i] * a[i];
+    return sqrt(s);
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric NP x NP matrix; eigenvalues sorted
+// descending (the order of singular values), eigenvectors in the columns of V.
+template <int NP>
+__device__ void jacobi_eig(double (&A)[NP][NP], double (&lam)[NP], double (&V)[NP][NP])
+{
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = 0; j < NP; j++) V[i][j] = (i == j) ? 1. : 0.;
+    for (int sweep = 0; sweep < 12; sweep++) {
+        double off = 0.;
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int q = p + 1; q < NP; q++) off += fabs(A[p][q]);
+        if (off == 0.) break;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+#pragma unroll
+            for (int q = p + 1; q < NP; q++) {
+                const double apq = A[p][q];
+                if (apq == 0.) continue;
+                if (fabs(apq) <= DBL_EPS * 1e-3 * sqrt(fabs(A[p][p] * A[q][q]))) {
+                    A[p][q] = A[q][p] = 0.;  // negligible against the scaled diagonal
+                    continue;
+                }
+                const double tau = (A[q][q] - A[p][p]) / (2. * apq);
+                const double t = (tau >= 0. ? 1. : -1.) / (fabs(tau) + sqrt(1. + tau * tau));
+                const double c = 1. / sqrt(1. + t * t), s = t * c;
+                A[p][p] -= t * apq;
+                A[q][q] += t * apq;
+                A[p][q] = A[q][p] = 0.;
+#pragma unroll
+                for (int r = 0; r < NP; r++) {
+                    if (r != p && r != q) {
+                        const double arp = A[r][p], arq = A[r][q];
+                        A[r][p] = A[p][r] = c * arp - s * arq;
+                        A[r][q] = A[q][r] = s * arp + c * arq;
+                    }
+                    const double vrp = V[r][p], vrq = V[r][q];
+                    V[r][p] = c * vrp - s * vrq;
+                    V[r][q] = s * vrp + c * vrq;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) lam[i] = A[i][i];
+    // sort descending (NP <= 3: bubble)
+#pragma unroll
+    for (int a = 0; a < NP - 1; a++)
+#pragma unroll
+        for (int b = 0; b < NP - 1 - a; b++)
+            if (lam[b] < lam[b + 1]) {
+                const double tl = lam[b];
+                lam[b] = lam[b + 1];
+                lam[b + 1] = tl;
+#pragma unroll
+                for (int r = 0; r < NP; r++) {
+                    const double tv = V[r][b];
+                    V[r][b] = V[r][b + 1];
+                    V[r][b + 1] = tv;
+                }
+            }
+}
+
+// scipy _lsq/common.py: CL_scaling_vector (all bounds finite here).
+template <int NP>
+__device__ __forceinline__ void cl_scaling(const double (&x)[NP], const double (&g)[NP], const double (&lb)[NP],
+                                           const double (&ub)[NP], double (&v)[NP], double (&dv)[NP])
+{
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        v[i] = 1.;
+        dv[i] = 0.;
+        if (g[i] < 0.) {
+            v[i] = ub[i] - x[i];
+            dv[i] = -1.;
+        }
+        if (g[i] > 0.) {
+            v[i] = x[i] - lb[i];
+            dv[i] = 1.;
+        }
+    }
+}
+
+// scipy _lsq/common.py: step_size_to_bound.
+template <int NP>
+__device__ __forceinline__ double step_to_bound(const double (&x)[NP], const double (&s)[NP], const double (&lb)[NP],
+                                                const double (&ub)[NP], int (&hits)[NP])
+{
+    double steps[NP], mn = INFINITY;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        steps[i] = INFINITY;
+        if (s[i] != 0.) steps[i] = fmax((lb[i] - x[i]) / s[i], (ub[i] - x[i]) / s[i]);
+        mn = fmin(mn, steps[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) hits[i] = (steps[i] == mn) ? ((s[i] > 0.) - (s[i] < 0.)) : 0;
+    return mn;
+}
+
+// 0.5 * s^T Bh s + g_h . s   (evaluate_quadratic with J_h^T J_h + diag folded into Bh)
+template <int NP>
+__device__ __forceinline__ double quad_form(const double (&Bh)[NP][NP], const double (&a)[NP], const double (&b)[NP])
+{
+    double q = 0.;
+#pragma unroll
+    for (int i = 0; i < NP; i++)
+#pragma unroll
+        for (int j = 0; j < NP; j++) q += a[i] * Bh[i][j] * b[j];
+    return q;
+}
+
+template <int NP>
+__device__ __forceinline__ double vdot(const double (&a)[NP], const double (&b)[NP])
+{
+    double s = 0.;
+#pragma unroll
+    for (int i = 0; i < NP; i++) s += a[i] * b[i];
+    return s;
+}
+
+// scipy _lsq/common.py: minimize_quadratic_1d (candidate order lb, ub, extremum; first minimum wins).
+__device__ __forceinline__ void min_quad_1d(double a, double b, double lo, double hi, double c, double &t, double &y)
+{
+    t = lo;
+    y = lo * (a * lo + b) + c;
+    const double yh = hi * (a * hi + b) + c;
+    if (yh < y) {
+        t = hi;
+        y = yh;
+    }
+    if (a != 0.) {
+        const double ex = -0.5 * b / a;
+        if (lo < ex && ex < hi) {
+            const double ye = ex * (a * ex + b) + c;
+            if (ye < y) {
+                t = ex;
+                y = ye;
+            }
+        }
+    }
+}
+
+// scipy _lsq/common.py: solve_lsq_trust_region, expressed with lam = s^2 and suf = V^T g_h.
+template <int NP>
+__device__ void solve_tr(int m, const double (&lam)[NP], const double (&V)[NP][NP], const double (&suf)[NP],
+                         double Delta, double &alpha, double (&p)[NP])
+{
+    double s[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) s[i] = sqrt(fmax(lam[i], 0.));
+    const bool full_rank = (m >= NP) && (s[NP - 1] > DBL_EPS * m * s[0]);
+    double w[NP];
+    if (full_rank) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) w[i] = suf[i] / lam[i];
+        if (vnorm<NP>(w) <= Delta) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) {
+                double a = 0.;
+#pragma unroll
+                for (int j = 0; j < NP; j++) a += V[i][j] * w[j];
+                p[i] = -a;
+            }
+            alpha = 0.;
+            return;
+        }
+    }
+    auto phi_dphi = [&](double al, double &phi, double &dphi) {
+        double pn2 = 0., d3 = 0.;
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            const double den = lam[i] + al;
+            const double q = suf[i] / den;
+            pn2 += q * q;
+            d3 += suf[i] * suf[i] / (den * den * den);
+        }
+        const double pn = sqrt(pn2);
+        phi = pn - Delta;
+        dphi = -d3 / pn;
+    };
+    double alpha_upper = vnorm<NP>(suf) / Delta, alpha_lower = 0.;
+    if (full_rank) {
+        double phi, dphi;
+        phi_dphi(0., phi, dphi);
+        alpha_lower = -phi / dphi;
+    }
+    if (!full_rank && alpha == 0.) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+    for (int it = 0; it < 10; it++) {
+        if (alpha < alpha_lower || alpha > alpha_upper)
+            alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+        double phi, dphi;
+        phi_dphi(alpha, phi, dphi);
+        if (phi < 0.) alpha_upper = alpha;
+        const double ratio = phi / dphi;
+        alpha_lower = fmax(alpha_lower, alpha - ratio);
+        alpha -= (phi + Delta) * ratio / Delta;
+        if (fabs(phi) < 0.01 * Delta) break;
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) w[i] = suf[i] / (lam[i] + alpha);
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        double a = 0.;
+#pragma unroll
+        for (int j = 0; j < NP; j++) a += V[i][j] * w[j];
+        p[i] = -a;
+    }
+    const double sc = Delta / vnorm<NP>(p);
+#pragma unroll
+    for (int i = 0; i < NP; i++) p[i] *= sc;
+}
+
+// scipy _lsq/trf.py: select_step.
+template <int NP>
+__device__ void select_step(const double (&x)[NP], const double (&Bh)[NP][NP], const double (&g_h)[NP],
+                            double (&p)[NP], double (&p_h)[NP], const double (&d)[NP], double Delta,
+                            const double (&lb)[NP], const double (&ub)[NP], double theta, double (&step)[NP],
+                            double (&step_h)[NP], double &predicted)
+{
+    bool inb = true;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const double xn = x[i] + p[i];
+        inb = inb && (xn >= lb[i]) && (xn <= ub[i]);
+    }
+    if (inb) {
+        const double pv = 0.5 * quad_form<NP>(Bh, p_h, p_h) + vdot<NP>(g_h, p_h);
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            step[i] = p[i];
+            step_h[i] = p_h[i];
+        }
+        predicted = -pv;
+        return;
+    }
+    int hits[NP], dummy[NP];
+    const double p_stride = step_to_bound<NP>(x, p, lb, ub, hits);
+    double r_h[NP], r[NP], xb[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        r_h[i] = hits[i] ? -p_h[i] : p_h[i];
+        r[i] = d[i] * r_h[i];
+        p[i] *= p_stride;
+        p_h[i] *= p_stride;
+        xb[i] = x[i] + p[i];
+    }
+    // intersect_trust_region(p_h, r_h, Delta): positive root of ||p_h + t r_h|| = Delta
+    double to_tr;
+    {
+        const double a = vdot<NP>(r_h, r_h), b = vdot<NP>(p_h, r_h), c = vdot<NP>(p_h, p_h) - Delta * Delta;
+        const double disc = sqrt(fmax(b * b - a * c, 0.));
+        const double q = -(b + copysign(disc, b));
+        const double t1 = q / a, t2 = c / q;
+        to_tr = fmax(t1, t2);
+    }
+    const double to_bound = step_to_bound<NP>(xb, r, lb, ub, dummy);
+    double r_stride = fmin(to_bound, to_tr), r_lo, r_hi;
+    if (r_stride > 0.) {
+        r_lo = (1. - theta) * p_stride / r_stride;
+        r_hi = (r_stride == to_bound) ? theta * to_bound : to_tr;
+    } else {
+        r_lo = 0.;
+        r_hi = -1.;
+    }
+    double r_value = INFINITY;
+    if (r_lo <= r_hi) {
+        const double a = 0.5 * quad_form<NP>(Bh, r_h, r_h);
+        const double b = vdot<NP>(g_h, r_h) + quad_form<NP>(Bh, p_h, r_h);
+        const double c = 0.5 * quad_form<NP>(Bh, p_h, p_h) + vdot<NP>(g_h, p_h);
+        min_quad_1d(a, b, r_lo, r_hi, c, r_stride, r_value);
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            r_h[i] = r_h[i] * r_stride + p_h[i];
+            r[i] = r_h[i] * d[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        p[i] *= theta;
+        p_h[i] *= theta;
+    }
+    const double p_value = 0.5 * quad_form<NP>(Bh, p_h, p_h) + vdot<NP>(g_h, p_h);
+    double ag_h[NP], ag[NP];
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        ag_h[i] = -g_h[i];
+        ag[i] = d[i] * ag_h[i];
+    }
+    const double tr2 = Delta / vnorm<NP>(ag_h);
+    const double tb2 = step_to_bound<NP>(x, ag, lb, ub, dummy);
+    double ag_stride = (tb2 < tr2) ? theta * tb2 : tr2, ag_value;
+    {
+        const double a = 0.5 * quad_form<NP>(Bh, ag_h, ag_h), b = vdot<NP>(g_h, ag_h);
+        min_quad_1d(a, b, 0., ag_stride, 0., ag_stride, ag_value);
+    }
+    if (p_value < r_value && p_value < ag_value) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            step[i] = p[i];
+            step_h[i] = p_h[i];
+        }
+        predicted = -p_value;
+    } else if (r_value < p_value && r_value < ag_value) {
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            step[i] = r[i];
+            step_h[i] = r_h[i];
+        }
+        predicted = -r_value;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NP; i++) {
+            step[i] = ag[i] * ag_stride;
+            step_h[i] = ag_h[i] * ag_stride;
+        }
+        predicted = -ag_value;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+}
+
+// ---- the fit kernel ---------------------------------------------------------------
+// G lanes per cell, NSL scales per lane (ns <= G*NSL), NP fitted parameters.
+template <int G, int NSL, int NP>
+__global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
+{
+    const int lane = threadIdx.x & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    const long long ncells = (long long)a.fx * a.fy;
+    const size_t nxy = (size_t)a.nx * a.ny;
+    const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
+    const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
+
+    // estimate.py:271,280,290,299
+    const double lb[3] = {2., 0.0001, 0.0001};
+    const double ub[3] = {250., 0.9999, FLEX_PI - 0.001};
+
+    for (long long cell = group; cell < ncells; cell += ngroups) {
+        const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
+        const int i = ci * a.nn, j = cj * a.nn;
+        const size_t src = (size_t)j * a.nx + i;
+        const size_t dst = (size_t)cj * a.mx + ci;
+        if (a.mask && a.mask[src]) continue;  // classes.py:1228-1231 (outputs stay zero)
+
+        const double rhoc = a.rhoc_map ? a.rhoc_map[src] : a.conf.rhoc;  // classes.py:1087-1091
+        const double zc = a.zc_map ? a.zc_map[src] : a.conf.zc;
+        const FlexCell fc = flex_cell(a.conf, rhoc, zc, a.wd[src]);
+
+        // per-lane data: scales lane, lane+G, ...
+        FlexK fk[NSL];
+        double ya[NSL], wa[NSL], yc[NSL], wc[NSL];
+        bool bad = false;
+#pragma unroll
+        for (int t = 0; t < NSL; t++) {
+            const int s = lane + t * G;
+            ya[t] = wa[t] = yc[t] = wc[t] = 0.;
+            fk[t].k4d = fk[t].top = fk[t].deep = 0.;
+            if (s < a.ns) {
+                fk[t] = flex_k(fc, a.k[s]);
+                const size_t o = src + nxy * s;
+                if (use_adm) {
+                    const double y = a.adm[o], e = a.eadm[o];
+                    bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                    ya[t] = y;
+                    wa[t] = 1. / e;  // curve_fit: transform = 1/sigma
+                }
+                if (use_coh) {
+                    const double y = a.coh[o], e = a.ecoh[o];
+                    bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                    yc[t] = y;
+                    wc[t] = 1. / e;
+                }
+            }
+        }
+        bad = __any_sync(gmask, bad);
+        if (bad) {  // SciPy raises ValueError here; we flag the cell
+            if (lane == 0) {
+                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                a.o_te[dst] = a.o_te_std[dst] = a.o_f[dst] = a.o_f_std[dst] = a.o_chi2[dst] = nanv;
+                if (NP == 3) a.o_a[dst] = a.o_a_std[dst] = nanv;
+                if (a.status) a.status[dst] = 3;
+            }
+            continue;
+        }
+
+        // residuals r = (model - y)/sigma; accumulate cost, J^T r, J^T J over the group's scales
+        auto evaluate = [&](const double(&x)[NP], Normal<NP> &nm) {
+            const double te = x[0], F = x[1];
+            const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
+            double sa, ca;
+            sincos(alpha, &sa, &ca);
+            const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+            double acc[1 + NP + NP * (NP + 1) / 2];
+#pragma unroll
+            for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
+#pragma unroll
+            for (int t = 0; t < NSL; t++) {
+                if (lane + t * G < a.ns) {
+                    double adm, coh, dA[3], dC[3];
+                    flex_eval<true>(fc, fk[t], te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+                    if (use_adm) {
+                        const double r = (adm - ya[t]) * wa[t];
+                        double jr[NP];
+#pragma unroll
+                        for (int p = 0; p < NP; p++) jr[p] = dA[p] * wa[t];
+                        acc[0] += r * r;
+                        int q = 1 + NP;
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+                            acc[1 + p] += jr[p] * r;
+#pragma unroll
+                            for (int p2 = p; p2 < NP; p2++) acc[q++] += jr[p] * jr[p2];
+                        }
+                    }
+                    if (use_coh) {
+                        const double r = (coh - yc[t]) * wc[t];
+                        double jr[NP];
+#pragma unroll
+                        for (int p = 0; p < NP; p++) jr[p] = dC[p] * wc[t];
+                        acc[0] += r * r;
+                        int q = 1 + NP;
+#pragma unroll
+                        for (int p = 0; p < NP; p++) {
+                            acc[1 + p] += jr[p] * r;
+#pragma unroll
+                            for (int p2 = p; p2 < NP; p2++) acc[q++] += jr[p] * jr[p2];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = group_sum<G>(acc[q], gmask);
+            nm.cost = 0.5 * acc[0];
+            int q = 1 + NP;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                nm.g[p] = acc[1 + p];
+#pragma unroll
+                for (int p2 = p; p2 < NP; p2++) {
+                    nm.B[p][p2] = acc[q];
+                    nm.B[p2][p] = acc[q];
+                    q++;
+                }
+            }
+        };
+
+        // ---- trf_bounds (scipy/optimize/_lsq/trf.py) ----
+        double x[NP], lbp[NP], ubp[NP];
+        const double x0[3] = {20., 0.5, FLEX_PI / 2.};  // estimate.py:271,290
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            x[p] = x0[p];
+            lbp[p] = lb[p];
+            ubp[p] = ub[p];
+        }
+        Normal<NP> cur, trial;
+        evaluate(x, cur);
+        int nfev = 1, status = -1;
+        double v[NP], dv[NP];
+        cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+        double Delta;
+        {
+            double t[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) t[p] = x[p] / sqrt(v[p]);
+            Delta = vnorm<NP>(t);
+            if (Delta == 0.) Delta = 1.;
+        }
+        double alpha = 0.;
+        if (!isfinite(cur.cost)) status = -3;  // "Residuals are not finite in the initial point"
+        while (status == -1) {
+            cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+            double g_norm = 0.;
+#pragma unroll
+            for (int p = 0; p < NP; p++) g_norm = fmax(g_norm, fabs(cur.g[p] * v[p]));
+            if (g_norm < TRF_GTOL) status = 1;
+            if (status != -1 || nfev >= TRF_MAX_NFEV) break;
+            double d[NP], diag_h[NP], g_h[NP], Bh[NP][NP], Bw[NP][NP], lam[NP], V[NP][NP], suf[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                d[p] = sqrt(v[p]);
+                diag_h[p] = cur.g[p] * dv[p];
+                g_h[p] = d[p] * cur.g[p];
+            }
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    Bh[p][q] = d[p] * d[q] * cur.B[p][q] + ((p == q) ? diag_h[p] : 0.);
+                    Bw[p][q] = Bh[p][q];
+                }
+            jacobi_eig<NP>(Bw, lam, V);
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                double s = 0.;
+#pragma unroll
+                for (int q = 0; q < NP; q++) s += V[q][p] * g_h[q];
+                suf[p] = s;
+            }
+            const double theta = fmax(0.995, 1. - g_norm);
+            double actual = -1., step_norm = 0.;
+            double xn[NP];
+            while (actual <= 0. && nfev < TRF_MAX_NFEV) {
+                double p_h[NP], pp[NP], step[NP], step_h[NP], predicted;
+                solve_tr<NP>(m, lam, V, suf, Delta, alpha, p_h);
+#pragma unroll
+                for (int p = 0; p < NP; p++) pp[p] = d[p] * p_h[p];
+                select_step<NP>(x, Bh, g_h, pp, p_h, d, Delta, lbp, ubp, theta, step, step_h, predicted);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {  // make_strictly_feasible(x + step, rstep=0)
+                    double t = x[p] + step[p];
+                    if (t <= lbp[p]) t = nextafter(lbp[p], ubp[p]);
+                    else if (t >= ubp[p]) t = nextafter(ubp[p], lbp[p]);
+                    xn[p] = t;
+                }
+                evaluate(xn, trial);
+                nfev++;
+                const double step_h_norm = vnorm<NP>(step_h);
+                if (!isfinite(trial.cost)) {
+                    Delta = 0.25 * step_h_norm;
+                    continue;
+                }
+                actual = cur.cost - trial.cost;
+                // update_tr_radius
+                double ratio, Delta_new = Delta;
+                if (predicted > 0.) ratio = actual / predicted;
+                else if (predicted == 0. && actual == 0.) ratio = 1.;
+                else ratio = 0.;
+                if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
+                else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
+                step_norm = vnorm<NP>(step);
+                // check_termination
+                const bool f_ok = (actual < TRF_FTOL * cur.cost) && (ratio > 0.25);
+                const bool x_ok = step_norm < TRF_XTOL * (TRF_XTOL + vnorm<NP>(x));
+                if (f_ok && x_ok) status = 4;
+                else if (f_ok) status = 2;
+                else if (x_ok) status = 3;
+                if (status != -1) break;
+                alpha *= Delta / Delta_new;
+                Delta = Delta_new;
+            }
+            if (actual > 0.) {
+#pragma unroll
+                for (int p = 0; p < NP; p++) x[p] = xn[p];
+                cur = trial;
+            }
+        }
+
+        // ---- covariance and outputs (curve_fit: _minpack_py.py:1050-1054, estimate.py:286-287,390) ----
+        if (lane == 0) {
+            double Bc[NP][NP], lam[NP], V[NP][NP], sd[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++)
+#pragma unroll
+                for (int q = 0; q < NP; q++) Bc[p][q] = cur.B[p][q];
+            jacobi_eig<NP>(Bc, lam, V);
+            const double s0 = sqrt(fmax(lam[0], 0.));
+            const double thr = DBL_EPS * (double)((m > NP) ? m : NP) * s0;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                double c = 0.;
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    const double sq = sqrt(fmax(lam[q], 0.));
+                    if (sq > thr) c += V[p][q] * V[p][q] / lam[q];
+                }
+                sd[p] = sqrt(c);
+            }
+            const double chi2 = 2. * cur.cost / (double)(m - NP);
+            a.o_te[dst] = x[0];
+            a.o_te_std[dst] = sd[0];
+            a.o_f[dst] = x[1];
+            a.o_f_std[dst] = sd[1];
+            if (NP == 3) {
+                a.o_a[dst] = x[NP - 1];
+                a.o_a_std[dst] = sd[NP - 1];
+            }
+            a.o_chi2[dst] = chi2;
+            if (a.status) a.status[dst] = (status > 0) ? 1 : ((status == -3) ? 3 : 2);
+        }
+    }
+}
+
+// Batched model curves (flex.real_xspec_functions for many parameter sets).
+__global__ void xspec_kernel(pfx_flex_conf conf, const double *__restrict__ k, int ns, int ncurves,
+                             const double *__restrict__ te, const double *__restrict__ f,
+                             const double *__restrict__ alpha, const double *__restrict__ wd,
+                             double *__restrict__ admit, double *__restrict__ coh, double *__restrict__ jac_admit,
+                             double *__restrict__ jac_coh)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)ncurves * ns) return;
+    const int c = (int)(t / ns), s = (int)(t % ns);
+    const FlexCell fc = flex_cell(conf, conf.rhoc, conf.zc, wd ? wd[c] : 0.);
+    const FlexK fk = flex_k(fc, k[s]);
+    const double T = te[c], F = f[c];
+    double sa, ca;
+    sincos(alpha[c], &sa, &ca);
+    double a, co, dA[3], dC[3];
+    flex_eval<true>(fc, fk, T, T * T * T, F / (1. - F), 1. / ((1. - F) * (1. - F)), ca, sa, a, co, dA, dC);
+    admit[t] = a;
+    coh[t] = co;
+    if (jac_admit)
+        for (int p = 0; p < 3; p++) jac_admit[((size_t)c * 3 + p) * ns + s] = dA[p];
+    if (jac_coh)
+        for (int p = 0; p < 3; p++) jac_coh[((size_t)c * 3 + p) * ns + s] = dC[p];
+}
+
+template <int G, int NSL>
+int launch_fit_np(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
+{
+    const long long ncells = (long long)a.fx * a.fy;
+    const int threads = 128;
+    long long blocks = (ncells * G + threads - 1) / threads;
+    const long long cap = (long long)nsm * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (alph)
+        fit_kernel<G, NSL, 3><<<(unsigned)blocks, threads, 0, stream>>>(a);
+    else
+        fit_kernel<G, NSL, 2><<<(unsigned)blocks, threads, 0, stream>>>(a);
+    PFX_CUDA(cudaGetLastError());
+    return PFX_OK;
+}
+
+}  // namespace
+
+}  // namespace pfx
+
+using namespace pfx;
+
+extern "C" {
+
+int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const double *k_dev, int ns, int nx, int ny,
+                   const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,
+                   const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn, int alph,
+                   int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std, double *out_alpha,
+                   double *out_alpha_std, double *out_chi2, int32_t *status)
+{
+    PFX_ARG(conf && k_dev, "conf or k is null");
+    PFX_ARG(ns >= 1 && ns <= 64, "ns must be in [1, 64]");
+    PFX_ARG(nx >= 1 && ny >= 1 && nn >= 1, "bad grid shape or decimator");
+    PFX_ARG(atype == PFX_ATYPE_ADMIT || atype == PFX_ATYPE_COH || atype == PFX_ATYPE_JOINT, "bad atype");
+    PFX_ARG(wl_admit && ewl_admit && wl_coh && ewl_coh && wd, "null input map");
+    PFX_ARG(out_te && out_te_std && out_f && out_f_std && out_chi2, "null output map");
+    PFX_ARG(!alph || (out_alpha && out_alpha_std), "alph set but alpha outputs are null");
+    const int np = alph ? 3 : 2;
+    const int m = ((atype == PFX_ATYPE_JOINT) ? 2 : 1) * ns;
+    PFX_ARG(m > np, "need more data points than parameters");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FitArgs a;
+    a.conf = *conf;
+    a.k = k_dev;
+    a.ns = ns;
+    a.nx = nx;
+    a.ny = ny;
+    a.adm = wl_admit;
+    a.eadm = ewl_admit;
+    a.coh = wl_coh;
+    a.ecoh = ewl_coh;
+    a.wd = wd;
+    a.rhoc_map = rhoc_map;
+    a.zc_map = zc_map;
+    a.mask = mask;
+    a.nn = nn;
+    a.atype = atype;
+    a.fx = (nx > nn) ? (nx - nn + nn - 1) / nn : 0;  // len(range(0, nx-nn, nn)), classes.py:1218
+    a.fy = (ny > nn) ? (ny - nn + nn - 1) / nn : 0;
+    a.mx = nx / nn;                                  // classes.py:1189
+    a.my = ny / nn;
+    a.o_te = out_te;
+    a.o_te_std = out_te_std;
+    a.o_f = out_f;
+    a.o_f_std = out_f_std;
+    a.o_a = out_alpha;
+    a.o_a_std = out_alpha_std;
+    a.o_chi2 = out_chi2;
+    a.status = status;
+    const size_t mo = (size_t)a.mx * a.my;
+    int rc = PFX_OK;
+    auto zero = [&](void *p, size_t bytes) {
+        if (p && rc == PFX_OK && cudaMemsetAsync(p, 0, bytes, st) != cudaSuccess) {
+            set_error("cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = PFX_ERR_CUDA;
+        }
+    };
+    zero(out_te, mo * 8);
+    zero(out_te_std, mo * 8);
+    zero(out_f, mo * 8);
+    zero(out_f_std, mo * 8);
+    zero(out_chi2, mo * 8);
+    if (alph) {
+        zero(out_alpha, mo * 8);
+        zero(out_alpha_std, mo * 8);
+    }
+    zero(status, mo * 4);
+    if (rc == PFX_OK && a.fx > 0 && a.fy > 0) {
+        // range(0, nx-nn, nn) never reaches index mx*nn or beyond (classes.py:1218 vs 1189)
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        if (ns <= 8)
+            rc = launch_fit_np<8, 1>(a, alph, st, nsm);
+        else if (ns <= 16)
+            rc = launch_fit_np<8, 2>(a, alph, st, nsm);
+        else if (ns <= 24)
+            rc = launch_fit_np<8, 3>(a, alph, st, nsm);
+        else if (ns <= 32)
+            rc = launch_fit_np<8, 4>(a, alph, st, nsm);
+        else if (ns <= 48)
+            rc = launch_fit_np<16, 3>(a, alph, st, nsm);
+        else
+            rc = launch_fit_np<16, 4>(a, alph, st, nsm);
+    }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return rc;
+}
+
+int pfx_l2_fit_host(int device, const pfx_flex_conf *conf, const double *k, int ns, int nx, int ny,
+                    const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,
+                    const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn, int alph,
+                    int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std, double *out_alpha,
+                    double *out_alpha_std, double *out_chi2, int32_t *status)
+{
+    PFX_ARG(k && nx >= 1 && ny >= 1 && ns >= 1 && nn >= 1, "bad arguments");
+    PFX_ARG(wl_admit && ewl_admit && wl_coh && ewl_coh && wd, "null input map");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    const size_t nxy = (size_t)nx * ny, cube = nxy * ns, mo = (size_t)(nx / nn) * (ny / nn);
+    std::vector<void *> bufs;
+    int rc = PFX_OK;
+    auto up = [&](const void *h, size_t bytes) -> void * {
+        if (!h || rc != PFX_OK) return nullptr;
+        void *d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device allocation of %zu bytes failed", bytes);
+            rc = PFX_ERR_OOM;
+            return nullptr;
+        }
+        bufs.push_back(d);
+        if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) {
+            set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = PFX_ERR_CUDA;
+        }
+        return d;
+    };
+    auto dn = [&](void *h, size_t bytes) -> void * {
+        if (!h || rc != PFX_OK) return nullptr;
+        void *d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("device allocation of %zu bytes failed", bytes);
+            rc = PFX_ERR_OOM;
+            return nullptr;
+        }
+        bufs.push_back(d);
+        return d;
+    };
+    const double *d_k = (const double *)up(k, ns * 8);
+    const double *d_a = (const double *)up(wl_admit, cube * 8), *d_ea = (const double *)up(ewl_admit, cube * 8);
+    const double *d_c = (const double *)up(wl_coh, cube * 8), *d_ec = (const double *)up(ewl_coh, cube * 8);
+    const double *d_wd = (const double *)up(wd, nxy * 8);
+    const double *d_rc = (const double *)up(rhoc_map, nxy * 8), *d_zc = (const double *)up(zc_map, nxy * 8);
+    const uint8_t *d_m = (const uint8_t *)up(mask, nxy);
+    double *o[7];
+    double *h[7] = {out_te, out_te_std, out_f, out_f_std, out_alpha, out_alpha_std, out_chi2};
+    for (int i = 0; i < 7; i++) o[i] = (double *)dn(h[i], mo * 8);
+    int32_t *d_st = (int32_t *)dn(status, mo * 4);
+    if (rc == PFX_OK)
+        rc = pfx_l2_fit_dev(device, nullptr, conf, d_k, ns, nx, ny, d_a, d_ea, d_c, d_ec, d_wd, d_rc, d_zc, d_m, nn, alph,
+                            atype, o[0], o[1], o[2], o[3], o[4], o[5], o[6], d_st);
+    if (rc == PFX_OK) {
+        for (int i = 0; i < 7; i++)
+            if (h[i]) cudaMemcpyAsync(h[i], o[i], mo * 8, cudaMemcpyDeviceToHost, 0);
+        if (status) cudaMemcpyAsync(status, d_st, mo * 4, cudaMemcpyDeviceToHost, 0);
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) {
+            set_error("fit failed: %s", cudaGetErrorString(e));
+            rc = PFX_ERR_CUDA;
+        }
+    }
+    for (void *p : bufs) cudaFree(p);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return rc;
+}
+
+int pfx_flex_xspec_host(int device, const pfx_flex_conf *conf, const double *k, int ns, int ncurves, const double *te,
+                        const double *f, const double *alpha, const double *wd, double *admit, double *coh,
+                        double *jac_admit, double *jac_coh)
+{
+    PFX_ARG(conf && k && te && f && alpha && admit && coh, "null pointer");
+    PFX_ARG(ns >= 1 && ncurves >= 1, "ns, ncurves must be >= 1");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t)ns * ncurves;
+    double *d = nullptr;
+    const size_t total = ns + 4 * (size_t)ncurves + 8 * n;
+    PFX_CUDA(cudaMalloc(&d, total * 8));
+    double *d_k = d, *d_te = d_k + ns, *d_f = d_te + ncurves, *d_al = d_f + ncurves, *d_wd = d_al + ncurves,
+           *d_adm = d_wd + ncurves, *d_coh = d_adm + n, *d_ja = d_coh + n, *d_jc = d_ja + 3 * n;
+    int rc = PFX_OK;
+    cudaMemcpyAsync(d_k, k, ns * 8, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(d_te, te, ncurves * 8, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(d_f, f, ncurves * 8, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(d_al, alpha, ncurves * 8, cudaMemcpyHostToDevice, 0);
+    if (wd) cudaMemcpyAsync(d_wd, wd, ncurves * 8, cudaMemcpyHostToDevice, 0);
+    xspec_kernel<<<(unsigned)((n + 127) / 128), 128>>>(*conf, d_k, ns, ncurves, d_te, d_f, d_al, wd ? d_wd : nullptr,
+                                                       d_adm, d_coh, jac_admit ? d_ja : nullptr,
+                                                       jac_coh ? d_jc : nullptr);
+    cudaMemcpyAsync(admit, d_adm, n * 8, cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(coh, d_coh, n * 8, cudaMemcpyDeviceToHost, 0);
+    if (jac_admit) cudaMemcpyAsync(jac_admit, d_ja, 3 * n * 8, cudaMemcpyDeviceToHost, 0);
+    if (jac_coh) cudaMemcpyAsync(jac_coh, d_jc, 3 * n * 8, cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("flex_xspec failed: %s", cudaGetErrorString(e));
+        rc = PFX_ERR_CUDA;
+    }
+    cudaFree(d);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// pfx_plan.hpp -- the CWT plan object behind the opaque pfx_plan handle.
+#pragma once
+#include <vector>
+
+#include "pfx_common.cuh"
+
+// Per-(scale) constants of the fan of daughters (cpwt.f90:131,148-161; cpwt_sub.f90:85-87).
+struct PfxScaleConsts {
+    double s;              // scale = k0 / (k*1e3)   [km]
+    double norm;           // s / sqrt(pi)
+    double kx0[PFX_NA];    // k0*cos(angle)
+    double ky0[PFX_NA];    // k0*sin(angle)
+    double e0[PFX_NA];     // exp(-0.5*(kx0^2 + ky0^2))
+};
+
+struct pfx_plan {
+    int nx = 0, ny = 0, ns = 0, NX = 0, NY = 0;
+    int engine = PFX_ENGINE_PRUNED, device = 0;
+    double dx = 0, dy = 0, k0 = 0, cutoff = 9.5;
+    std::vector<double> k;               // rad/m
+    std::vector<PfxScaleConsts> consts;  // per scale
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    size_t device_bytes = 0;
+
+    // wavenumber axes (defk, cpwt_sub.f90:41-62) and the scale-independent
+    // admissibility factors exp(-kx^2/2), exp(-ky^2/2) (cpwt_sub.f90:93)
+    double *d_kx = nullptr, *d_ky = nullptr, *d_u2 = nullptr, *d_v2 = nullptr;
+    // padded spectra of up to two grids, layout [b][a] (a = x-wavenumber fastest)
+    double2 *d_spec[2] = {nullptr, nullptr};
+    double *d_partial = nullptr;  // deterministic two-stage sum for the mean
+    cufftHandle fft_fwd = 0;
+    bool fft_fwd_ok = false;
+
+    // dense engine: per-scale separable daughter tables u1[11][NX], v1[11][NY], and 22 work planes
+    double *d_tab = nullptr;
+    double2 *d_planes = nullptr;
+    cufftHandle fft_inv[2] = {0, 0};  // batch 11 and batch 22
+    bool fft_inv_ok[2] = {false, false};
+    void *d_fft_work = nullptr;
+    size_t fft_work_bytes = 0;
+
+    // grow-only scratch used by the _host entry points (inputs / outputs staging)
+    void *d_scratch[8] = {};
+    size_t scratch_bytes[8] = {};
+
+    std::vector<void *> owned;  // everything to cudaFree on destroy
+
+    int alloc(void **p, size_t bytes);
+    int scratch(int slot, size_t bytes, void **p);
+};
+
+namespace pfx {
+
+// K1: mirror + de-mean + zero-pad (cpwt.f90:100-116, cpwt_sub.f90:435-449) then one forward FFT
+// (cpwt.f90:122) of grid g (device pointer, C order) into plan->d_spec[slot].
+int forward_spectrum(pfx_plan *pl, const double *grid_dev, int slot);
+
+// Dense engine: all 11 azimuth planes of scale `is` for ngrids spectra -> plan->d_planes
+// (plane p = ia + 11*g), as un-normalised, un-shifted inverse FFTs.
+int dense_scale_planes(pfx_plan *pl, int is, int ngrids);
+PlaneView dense_view(const pfx_plan *pl, int g);
+
+int plan_init_dense(pfx_plan *pl);
+
+}  // namespace pfx

@@ -1,0 +1,214 @@
+// pfx_reduce.cu -- K3: azimuth reduction, admittance / coherence and the
+// running-prefix jackknife, one thread per grid cell, all 11 azimuths of the
+// cell held in registers.  Replaces the full-cube passes of
+//   cpwt.f90:200-241 (wlet_scalogram), 250-293 (wlet_xscalogram), 303-364
+//   (wlet_admit_coh) and cpwt_sub.f90:107-160, 298-366 (the jackknives)
+// without ever materialising the (nx,ny,na,ns) temporaries sg/sg1/sg2/xsg.
+//
+// HBM traffic per cell and scale: 11 (or 22) coalesced 16-byte loads and 2-4
+// 8-byte stores; consecutive threads own consecutive x so every warp reads and
+// writes whole 128-byte lines.
+#include "pfx_common.cuh"
+
+namespace pfx {
+
+namespace {
+
+constexpr int NA = PFX_NA;
+
+__device__ __forceinline__ double jk_spread(const double (&v2)[NA])
+{
+    // cpwt_sub.f90:144-152 / 344-357: mean of the NA delete-one values, then
+    // sqrt((na-1)/na * sum (v - mean)^2), NaN -> 0.
+    double m = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) m += v2[a];
+    m = m / (double)NA;
+    double d = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) d = d + (v2[a] - m) * (v2[a] - m);
+    d = sqrt(d * (double)(NA - 1) / (double)NA);
+    return (d != d) ? 0.0 : d;
+}
+
+// cpwt_sub.f90:107-160.  For the left-out azimuth a the reference walks the
+// other ten in order and averages the ten running sums.  The partial sums over
+// azimuths < a are the same for every a, so the walk for a resumes from the
+// shared prefix; additions happen in the reference's order.
+__device__ __forceinline__ double jk_sgram(const double (&s)[NA])
+{
+    double v2[NA];
+    double p = 0.0, cum = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        double q = p, acc = cum;
+#pragma unroll
+        for (int a2 = a + 1; a2 < NA; a2++) {
+            q += s[a2];
+            acc += q;
+        }
+        v2[a] = acc / (double)(NA - 1);
+        if (a < NA - 1) {
+            p += s[a];
+            cum += p;
+        }
+    }
+    return jk_spread(v2);
+}
+
+__device__ __forceinline__ void ratio(double q1, double q2, double qx, double &ad, double &co)
+{
+    // cpwt_sub.f90:329-335
+    if (q1 != 0.0 && q2 != 0.0) {
+        co = qx * qx / (q1 * q2);
+        ad = qx / q1;
+    } else {
+        co = 0.0;
+        ad = 0.0;
+    }
+}
+
+// cpwt_sub.f90:298-366, same shared-prefix walk: 10 + 55 ratio evaluations
+// instead of the reference's 110.
+__device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const double (&s2)[NA], const double (&xr)[NA],
+                                             double &ead, double &eco)
+{
+    double ad2[NA], co2[NA];
+    double p1 = 0.0, p2 = 0.0, px = 0.0, cad = 0.0, cco = 0.0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        double q1 = p1, q2 = p2, qx = px, sa = cad, sc = cco;
+#pragma unroll
+        for (int a2 = a + 1; a2 < NA; a2++) {
+            q1 += s1[a2];
+            q2 += s2[a2];
+            qx += xr[a2];
+            double ad, co;
+            ratio(q1, q2, qx, ad, co);
+            sa += ad;
+            sc += co;
+        }
+        ad2[a] = sa / (double)(NA - 1);
+        co2[a] = sc / (double)(NA - 1);
+        if (a < NA - 1) {
+            p1 += s1[a];
+            p2 += s2[a];
+            px += xr[a];
+            double ad, co;
+            ratio(p1, p2, px, ad, co);
+            cad += ad;
+            cco += co;
+        }
+    }
+    ead = jk_spread(ad2);
+    eco = jk_spread(co2);
+}
+
+__device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int j)
+{
+    const double2 w = __ldg(v.base + (size_t)p * v.plane_stride + (size_t)(j + v.off_j) * v.ld + (i + v.off_i));
+    return make_double2(w.x * v.scale, w.y * v.scale);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+    reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
+                  double *__restrict__ out2, double *__restrict__ out3)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= nx) return;
+    const size_t o = (size_t)j * nx + i;
+
+    if (MODE == RED_SCALOGRAM) {
+        double s[NA];
+        double tot = 0.0;
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            const double2 w = load_w(w1, a, i, j);
+            s[a] = fabs(w.x * w.x + w.y * w.y);  // CABS(w*CONJG(w)), cpwt.f90:224
+            tot += s[a];
+        }
+        out0[o] = tot / (double)NA;  // cpwt.f90:234
+        out1[o] = jk_sgram(s);
+    } else if (MODE == RED_XSCALOGRAM) {
+        double xr[NA], xi[NA];
+        double tr = 0.0, ti = 0.0;
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            const double2 u = load_w(w1, a, i, j), v = load_w(w2, a, i, j);
+            xr[a] = u.x * v.x + u.y * v.y;  // w1*CONJG(w2), cpwt.f90:274
+            xi[a] = u.y * v.x - u.x * v.y;
+            tr += xr[a];
+            ti += xi[a];
+        }
+        reinterpret_cast<double2 *>(out0)[o] = make_double2(tr / (double)NA, ti / (double)NA);
+        const double er = jk_sgram(xr), ei = jk_sgram(xi);
+        out1[o] = sqrt(er * er + ei * ei);  // cpwt.f90:290
+    } else {
+        double s1[NA], s2[NA], xr[NA];
+        double t1 = 0.0, t2 = 0.0, tx = 0.0;
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            const double2 u = load_w(w1, a, i, j), v = load_w(w2, a, i, j);
+            s1[a] = fabs(u.x * u.x + u.y * u.y);  // cpwt.f90:333
+            s2[a] = fabs(v.x * v.x + v.y * v.y);  // cpwt.f90:334
+            xr[a] = u.x * v.x + u.y * v.y;        // Re(w1*CONJG(w2)), cpwt.f90:335
+            t1 += s1[a];
+            t2 += s2[a];
+            tx += xr[a];
+        }
+        t1 = t1 / (double)NA;  // cpwt.f90:348-350
+        t2 = t2 / (double)NA;
+        tx = tx / (double)NA;
+        out0[o] = tx / t1;                // cpwt.f90:354
+        out2[o] = (tx * tx) / (t1 * t2);  // cpwt.f90:355
+        double ead, eco;
+        jk_admit_coh(s1, s2, xr, ead, eco);
+        out1[o] = ead;
+        out3[o] = eco;
+    }
+}
+
+__global__ void crop_kernel(int nx, int ny, PlaneView w, double2 *__restrict__ slab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int p = blockIdx.z;
+    if (i >= nx) return;
+    slab[((size_t)p * ny + j) * nx + i] = load_w(w, p, i, j);
+}
+
+}  // namespace
+
+int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
+                  double *out3, cudaStream_t stream)
+{
+    dim3 block(128), grid((nx + 127) / 128, ny);
+    switch (mode) {
+        case RED_SCALOGRAM:
+            reduce_kernel<RED_SCALOGRAM><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            break;
+        case RED_XSCALOGRAM:
+            reduce_kernel<RED_XSCALOGRAM><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            break;
+        case RED_ADMIT_COH:
+            reduce_kernel<RED_ADMIT_COH><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            break;
+        default:
+            set_error("launch_reduce: bad mode %d", mode);
+            return PFX_ERR_ARG;
+    }
+    PFX_CUDA(cudaGetLastError());
+    return PFX_OK;
+}
+
+int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream)
+{
+    dim3 block(128), grid((nx + 127) / 128, ny, PFX_NA);
+    crop_kernel<<<grid, block, 0, stream>>>(nx, ny, w, slab);
+    PFX_CUDA(cudaGetLastError());
+    return PFX_OK;
+}
+
+}  // namespace pfx

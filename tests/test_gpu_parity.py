@@ -1,0 +1,299 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the float64 CPU oracle on the same seeded inputs, against the committed golden
+fixtures, and through size-independent properties at BASELINE sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import A_TOL, CHI2_RTOL, F_TOL, STD_RTOL, TE_TOL, assert_maps_close, red_field
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ENGINES = ["dense"]
+
+
+@pytest.fixture(params=ENGINES)
+def engine(request, monkeypatch, pf):
+    from plateflex_b200 import _lib
+    monkeypatch.setenv("PLATEFLEX_B200_ENGINE", request.param)
+    _lib.clear_plans()
+    yield request.param
+    _lib.clear_plans()
+
+
+CASES = [  # nx, ny, dx, dy, wavenumbers (rad/m)
+    (32, 32, 5.0, 5.0, [2e-5, 8e-5, 3e-4]),
+    (44, 37, 20.0, 18.0, [1.2e-5, 2.5e-5, 5.0e-5, 9.0e-5]),
+    (17, 50, 20.0, 7.0, [1.5e-5, 6e-5]),
+    (64, 48, 10.0, 10.0, None),  # natural wavenumber ladder of the grid (classes._lam2k)
+    (2, 3, 10.0, 10.0, [5e-5]),
+]
+
+
+@pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES)
+def test_wlet_transform_matches_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
+    from plateflex_b200 import classes
+    from plateflex_b200.cpwt import cpwt
+    g = red_field(nx, ny, seed=nx * 100 + ny) * 400.0 + 37.0
+    kf = np.array(kf) if kf is not None else classes._lam2k(nx, ny, dx, dy)[1]
+    got = cpwt.wlet_transform(g, dx, dy, kf)
+    ref = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0, prec=64)
+    assert got.shape == ref.shape == (nx, ny, 11, len(kf)) and got.dtype == np.complex128
+    assert got.flags.f_contiguous
+    for s in range(len(kf)):
+        for part in (np.real, np.imag):
+            assert_maps_close(part(got[..., s]), part(ref[..., s]), f"wl_trans[{s}]",
+                              rtol=1e-9, atol_rel=1e-12 * 1e3)
+
+
+@pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[:4])
+def test_fused_reductions_match_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
+    from plateflex_b200 import classes
+    from plateflex_b200.cpwt import fused
+    t = red_field(nx, ny, seed=1) * 500.0
+    g = 0.08 * t + red_field(nx, ny, seed=2) * 20.0
+    kf = np.array(kf) if kf is not None else classes._lam2k(nx, ny, dx, dy)[1]
+    w1 = ora.wlet_transform(t, dx, dy, kf, k0=pf.cf_wt.k0)
+    w2 = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0)
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), fused.wlet_admit_coh(t, g, dx, dy, kf),
+                          ora.wlet_admit_coh(w1, w2)):
+        assert_maps_close(a, b, name)
+    for name, a, b in zip(("wl_sg", "ewl_sg"), fused.wlet_scalogram(t, dx, dy, kf), ora.wlet_scalogram(w1)):
+        assert_maps_close(a, b, name)
+    xs, exs = fused.wlet_xscalogram(t, g, dx, dy, kf)
+    rxs, rexs = ora.wlet_xscalogram(w1, w2)
+    assert_maps_close(xs.real, rxs.real, "wl_xsg.real", atol_rel=1e-11)
+    assert_maps_close(xs.imag, rxs.imag, "wl_xsg.imag", atol_rel=1e-11)
+    assert_maps_close(exs, rexs, "ewl_xsg")
+
+
+def test_scale_subrange(pf, ora, engine):
+    from plateflex_b200.cpwt import fused
+    t, g = red_field(40, 40, 3) * 500, red_field(40, 40, 4) * 30
+    kf = np.array([1e-5, 2e-5, 4e-5, 8e-5, 1.6e-4])
+    full = fused.wlet_admit_coh(t, g, 10., 10., kf)
+    part = fused.wlet_admit_coh(t, g, 10., 10., kf, scales=(1, 4))
+    for a, b in zip(full, part):
+        assert b.shape == (40, 40, 3) and np.array_equal(a[..., 1:4], b)
+
+
+def test_cube_input_forms_match_oracle(pf, ora):
+    from plateflex_b200.cpwt import cpwt
+    rng = np.random.default_rng(9)
+    shp = (13, 9, 11, 3)
+    w1 = rng.standard_normal(shp) + 1j * rng.standard_normal(shp)
+    w2 = 0.4 * w1 + 0.2 * (rng.standard_normal(shp) + 1j * rng.standard_normal(shp))
+    for a, b in zip(cpwt.wlet_admit_coh(w1, w2), ora.wlet_admit_coh(w1, w2)):
+        assert a.flags.f_contiguous and np.allclose(a, b, rtol=1e-12, atol=1e-14)
+    for a, b in zip(cpwt.wlet_scalogram(w1), ora.wlet_scalogram(w1)):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+    for a, b in zip(cpwt.wlet_xscalogram(w1, w2), ora.wlet_xscalogram(w1, w2)):
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        cpwt.wlet_scalogram(w1[:, :, :5, :])
+
+
+def test_golden_cwt_fixture(pf, engine):
+    from plateflex_b200.cpwt import cpwt, fused
+    z = np.load(os.path.join(GOLD, "cwt_small.npz"))
+    pf.cf_wt.k0 = float(z["k0"])
+    dx, dy = float(z["dx"]), float(z["dy"])
+    w = cpwt.wlet_transform(z["topo"], dx, dy, z["k"])
+    sel = w[:, :, z["ia_sel"], :]
+    assert np.abs(sel - z["wl_trans_topo_sel"]).max() <= 1e-9 * np.abs(z["wl_trans_topo_sel"]).max()
+    for name, got in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"),
+                         fused.wlet_admit_coh(z["topo"], z["grav"], dx, dy, z["k"])):
+        assert_maps_close(got, z[name], name)
+    for name, got in zip(("wl_sg", "ewl_sg"), fused.wlet_scalogram(z["topo"], dx, dy, z["k"])):
+        assert_maps_close(got, z[name], name)
+    pf.set_conf_cpwt()
+
+
+def test_zero_grid_gives_nan_admittance_and_zero_errors(pf, engine):
+    from plateflex_b200.cpwt import fused
+    z = np.zeros((16, 16))
+    adm, eadm, coh, ecoh = fused.wlet_admit_coh(z, z, 10., 10., np.array([5e-5]))
+    assert np.isnan(adm).all() and np.isnan(coh).all() and (eadm == 0).all() and (ecoh == 0).all()
+
+
+def test_flex_model_matches_oracle(pf, ora):
+    from plateflex_b200.flex import conf_flex, flex
+    f = np.load(os.path.join(GOLD, "flex_curves.npz"))
+    pf.set_conf_flex()
+    conf_flex.boug, conf_flex.rhoc, conf_flex.zc = int(f["boug"]), float(f["rhoc"]), float(f["zc"])
+    adm, coh, ja, jc = flex.real_xspec_batch(f["k"], f["te"], f["f"], f["alpha"], f["wd"], jac=True)
+    assert np.allclose(adm, f["admit"], rtol=1e-12, atol=0) and np.allclose(coh, f["coh"], rtol=1e-12, atol=1e-300)
+    # the single-curve f2py signature, with the rhof side effect of flex.f90:207-211
+    conf_flex.wd = float(f["wd"][1])
+    a1, c1 = flex.real_xspec_functions(f["k"], f["te"][1], f["f"][1], f["alpha"][1])
+    assert np.allclose(a1, f["admit"][1], rtol=1e-12) and conf_flex.rhof == conf_flex.rhow
+    # analytic Jacobian against central differences of the oracle
+    for c in (0, 3, 7):
+        conf = ora.FlexConf(wd=float(f["wd"][c]), boug=int(f["boug"]), rhoc=float(f["rhoc"]), zc=float(f["zc"]))
+        p = np.array([f["te"][c], f["f"][c], f["alpha"][c]])
+        for j in range(3):
+            h = 1e-6 * max(1.0, abs(p[j]))
+            pp, pm = p.copy(), p.copy()
+            pp[j] += h
+            pm[j] -= h
+            ap, cp = ora.real_xspec_functions(f["k"], *pp, conf)
+            am, cm = ora.real_xspec_functions(f["k"], *pm, conf)
+            da, dc = (ap - am) / (2 * h), (cp - cm) / (2 * h)
+            assert np.allclose(ja[c, j], da, rtol=2e-6, atol=1e-9 * np.abs(da).max() + 1e-300)
+            assert np.allclose(jc[c, j], dc, rtol=2e-6, atol=1e-9 * np.abs(dc).max() + 1e-300)
+    pf.set_conf_flex()
+
+
+def _compare_fit(got_mean, got_std, got_chi2, ref_mean, ref_std, ref_chi2, npar):
+    lo, hi = np.array([2., 1e-4, 1e-4])[:npar], np.array([250., 0.9999, np.pi - 1e-3])[:npar]
+    on_bound = np.any((ref_mean[:npar] - lo < 1e-3 * (hi - lo)) | (hi - ref_mean[:npar] < 1e-3 * (hi - lo)))
+    assert got_chi2 == pytest.approx(ref_chi2, rel=CHI2_RTOL if not on_bound else 1e-3)
+    if on_bound:
+        return False
+    tol = [TE_TOL, F_TOL, A_TOL][:npar]
+    for j in range(npar):
+        assert abs(got_mean[j] - ref_mean[j]) < tol[j], (j, got_mean, ref_mean)
+        assert got_std[j] == pytest.approx(ref_std[j], rel=STD_RTOL), (j, got_std, ref_std)
+    return True
+
+
+@pytest.mark.parametrize("atype", ["joint", "admit", "coh"])
+@pytest.mark.parametrize("alph", [False, True])
+def test_fit_matches_scipy_trf_golden(pf, atype, alph):
+    """Golden vectors: SciPy curve_fit (TRF) on the oracle model, tests/golden/make_golden.py."""
+    from plateflex_b200 import estimate
+    z = np.load(os.path.join(GOLD, "l2fit_cells.npz"))
+    pf.set_conf_flex()
+    n, ns = z["adm"].shape
+    # all cells at once: lay them along x of an (n+1, 2, ns) grid (last row/column is never fitted)
+    def lay(a):
+        m = np.ones((n + 1, 2, ns), order="F")
+        m[:n, 0, :] = a
+        return m
+    res = estimate.L2_estimate_grid(z["k"], lay(z["adm"]), lay(z["eadm"]), lay(z["coh"]), lay(z["ecoh"]),
+                                    wd=np.zeros((n + 1, 2)), nn=1, alph=alph, atype=atype)
+    assert (res["status"][:n, 0] == 1).all() and (res["status"][n:, :] == 0).all()
+    tag = f"{atype}_{int(alph)}"
+    npar = 3 if alph else 2
+    interior = 0
+    for c in range(n):
+        gm = [res["mean_Te"][c, 0], res["mean_F"][c, 0]] + ([res["mean_a"][c, 0]] if alph else [])
+        gs = [res["std_Te"][c, 0], res["std_F"][c, 0]] + ([res["std_a"][c, 0]] if alph else [])
+        interior += _compare_fit(gm, gs, res["chi2"][c, 0], z[tag + "_mean"][c], z[tag + "_std"][c],
+                                 float(z[tag + "_chi2"][c]), npar)
+    assert interior >= n // 2
+    # the single-cell entry point returns the reference's summary frame
+    s = estimate.L2_estimate_cell(z["k"], z["adm"][0], z["eadm"][0], z["coh"][0], z["ecoh"][0], alph, atype)
+    assert list(s.index) == ["Te", "F"] + (["alpha"] if alph else []) and list(s.columns) == ["mean", "std", "chi2"]
+    assert s.loc["Te", "mean"] == res["mean_Te"][0, 0]
+    assert len(estimate.get_L2_estimates(s)) == (7 if alph else 5)
+
+
+def test_fit_flags_bad_cells(pf):
+    from plateflex_b200 import estimate
+    z = np.load(os.path.join(GOLD, "l2fit_cells.npz"))
+    ns = len(z["k"])
+    def lay(v):
+        m = np.ones((3, 2, ns), order="F")
+        m[0, 0], m[1, 0] = v, v
+        return m
+    eadm = lay(z["eadm"][0])
+    eadm[1, 0, 3] = 0.0  # zero sigma: SciPy would raise (estimate.py:274)
+    with pytest.warns(RuntimeWarning):
+        res = estimate.L2_estimate_grid(z["k"], lay(z["adm"][0]), eadm, lay(z["coh"][0]), lay(z["ecoh"][0]),
+                                        wd=np.zeros((3, 2)))
+    assert res["status"][0, 0] == 1 and res["status"][1, 0] == 3 and np.isnan(res["mean_Te"][1, 0])
+    with pytest.raises(ValueError):
+        estimate.L2_estimate_grid(z["k"], lay(z["adm"][0]), eadm, lay(z["coh"][0]), lay(z["ecoh"][0]),
+                                  wd=np.zeros((3, 2)), strict=True)
+
+
+def test_project_end_to_end_matches_oracle_pipeline(pf, ora, engine):
+    """Grid -> Project.init -> wlet_admit_coh -> estimate_grid against oracle CWT + SciPy TRF."""
+    from oracle import l2fit
+    from plateflex_b200 import synthetic
+    pf.set_conf_cpwt()
+    pf.set_conf_flex()
+    nx, ny, dx, dy = 48, 40, 20.0, 20.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240002, Te=30.0, F=0.5)
+    t, b = pf.TopoGrid(topo.copy(), dx, dy), pf.BougGrid(grav, dx, dy)
+    mask = np.zeros((nx, ny), dtype=bool)
+    mask[8:16, 8:16] = True
+    proj = pf.Project(grids=[t, b])
+    proj.mask = mask
+    proj.init()
+    proj.wlet_admit_coh()
+    ref = ora.admit_coh_from_grids(t.data, b.data, dx, dy, proj.k, k0=pf.cf_wt.k0)
+    for name, r in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), ref):
+        assert_maps_close(getattr(proj, name), r, name)
+    nn = 8
+    proj.estimate_grid(nn=nn, atype="joint")
+    assert proj.mean_Te_grid.shape == (nx // nn, ny // nn) == proj.new_mask_grid.shape
+    assert proj.new_mask_grid[1, 1] and not proj.new_mask_grid[0, 0]
+    checked = 0
+    for ci, i in enumerate(range(0, nx - nn, nn)):
+        for cj, j in enumerate(range(0, ny - nn, nn)):
+            if mask[i, j]:
+                assert proj.mean_Te_grid[ci, cj] == 0 and proj.status_grid[ci, cj] == 0
+                continue
+            r = l2fit.L2_estimate_cell(proj.k, ref[0][i, j], ref[1][i, j], ref[2][i, j], ref[3][i, j],
+                                       conf=ora.FlexConf())
+            gm = [proj.mean_Te_grid[ci, cj], proj.mean_F_grid[ci, cj]]
+            gs = [proj.std_Te_grid[ci, cj], proj.std_F_grid[ci, cj]]
+            checked += _compare_fit(gm, gs, proj.chi2_grid[ci, cj], r["mean"], r["std"], r["chi2"], 2)
+    assert checked >= 5
+    # decimated maps keep zeros in the never-visited last row / column when nn divides the size
+    assert (proj.mean_Te_grid[-1, :] == 0).all() and (proj.mean_Te_grid[:, -1] == 0).all()
+    s = proj.estimate_cell(cell=(0, 0), returned=True)
+    assert s.loc["Te", "mean"] == proj.mean_Te_grid[0, 0]
+
+
+def test_wlet_scalogram_paths_agree_like_the_reference_docstring(pf, engine):
+    # classes.py:251-273: np.allclose(grid1.wl_sg, grid2.wl_sg) with and without a prior wlet_transform()
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((40, 40))
+    g1, g2 = pf.Grid(data, 10., 10.), pf.Grid(data, 10., 10.)
+    g1.wlet_scalogram()
+    g2.wlet_transform()
+    g2.wlet_scalogram()
+    assert g2.wl_trans.shape == (40, 40, 11, g2.ns) and g1.wl_sg.shape == (40, 40, g1.ns)
+    assert np.allclose(g1.wl_sg, g2.wl_sg, rtol=1e-12) and np.allclose(g1.ewl_sg, g2.ewl_sg, rtol=1e-10)
+
+
+@pytest.mark.parametrize("n", [1024])
+def test_full_size_properties(pf, engine, n):
+    """BASELINE configs[1] size (1024^2, 5 km): properties that need no oracle.
+    Linearity of the transform, scalogram == azimuth mean of |W|^2, admittance of a scaled copy."""
+    from plateflex_b200 import classes
+    from plateflex_b200.cpwt import cpwt, fused
+    from plateflex_b200 import synthetic
+    topo, grav = synthetic.make_pair(n, n, 5.0, 5.0, seed=20240000 + n)
+    k = classes._lam2k(n, n, 5.0, 5.0)[1][[0, 9, 19]]
+    wa = cpwt.wlet_transform(topo, 5.0, 5.0, k)
+    wb = cpwt.wlet_transform(grav, 5.0, 5.0, k)
+    wc = cpwt.wlet_transform(2.0 * topo - 3.0 * grav, 5.0, 5.0, k)
+    for s in range(3):
+        scale = max(np.abs(wa[..., s]).max() * 2, np.abs(wb[..., s]).max() * 3)
+        assert np.abs(wc[..., s] - (2.0 * wa[..., s] - 3.0 * wb[..., s])).max() <= 1e-11 * scale
+    sg, _ = fused.wlet_scalogram(topo, 5.0, 5.0, k)
+    assert np.allclose(sg, (np.abs(wa) ** 2).mean(axis=2), rtol=1e-11, atol=1e-13 * sg.max())
+    adm, eadm, coh, ecoh = fused.wlet_admit_coh(topo, 0.05 * topo, 5.0, 5.0, k)
+    assert np.allclose(adm, 0.05, rtol=1e-10) and np.allclose(coh, 1.0, rtol=1e-10)
+    assert np.abs(eadm).max() < 1e-10 and np.abs(ecoh).max() < 1e-10
+
+
+def test_dense_and_pruned_engines_agree_at_full_size(pf, monkeypatch):
+    from plateflex_b200 import _lib, classes, synthetic
+    from plateflex_b200.cpwt import fused
+    n = 1024
+    topo, grav = synthetic.make_pair(n, n, 5.0, 5.0, seed=20240000 + n)
+    k = classes._lam2k(n, n, 5.0, 5.0)[1][:20][[0, 5, 10, 15, 19]]
+    res = {}
+    for eng in ENGINES:
+        monkeypatch.setenv("PLATEFLEX_B200_ENGINE", eng)
+        _lib.clear_plans()
+        res[eng] = fused.wlet_admit_coh(topo, grav, 5.0, 5.0, k)
+    _lib.clear_plans()
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), res["pruned"], res["dense"]):
+        assert_maps_close(a, b, name)

@@ -1,0 +1,115 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU work is issued)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return json.load(open(os.path.join(GOLD, "lam2k_kat.json")))
+
+
+def test_lam2k_docstring_known_answer(pf, kat):
+    from plateflex_b200 import classes
+    d = kat["docstring"]  # classes.py:1787-1796
+    ns, k = classes._lam2k(d["nx"], d["ny"], d["dx"], d["dy"])
+    assert ns == d["ns"] == len(k)
+    assert np.allclose(k, d["k"], rtol=5e-8, atol=0)  # printed with 9 digits; k0 is float32-valued
+
+
+def test_lam2k_notebook_known_answer(pf, kat):
+    from plateflex_b200 import classes
+    d = kat["notebook_ex1"]  # Ex1_making_grids.ipynb cell 12
+    ns, k = classes._lam2k(d["nx"], d["ny"], d["dx"], d["dy"])
+    assert ns == d["ns"]
+    assert np.allclose(k, d["k"], rtol=6e-9, atol=0)  # matches only with the float32 k0
+    for s in kat["docstring_shapes"]:  # classes.py:209-220, 251-273
+        assert classes._lam2k(s["nx"], s["ny"], s["dx"], s["dy"])[0] == s["ns"]
+
+
+def test_k0_is_float32_valued(pf):
+    assert pf.cf_wt.k0 == float(np.float32(5.336)) != 5.336
+    assert pf.cf_wt.na == 11
+
+
+def test_conf_flex_defaults(pf):
+    pf.set_conf_flex()
+    c = pf.cf_fl
+    assert (c.zc, c.rhom, c.rhoc, c.rhow, c.rhoa, c.rhof, c.wd, c.boug) == (35e3, 3200., 2700., 1030., 0., 0., 0., 1)
+    assert (c.pi, c.g, c.em, c.nu, c.gc) == (3.141592653589793, 9.81, 1e11, 0.25, 6.67e-6)
+
+
+def test_grid_attributes_and_unit_scaling(pf):
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((30, 20))
+    g = pf.Grid(data, 10.0, 12.0)
+    assert (g.nx, g.ny, g.dx, g.dy) == (30, 20, 10.0, 12.0) and g.ns == len(g.k)
+    assert g.data is not data and np.array_equal(g.data, data)
+    assert not hasattr(g, "wl_trans")
+    topo_km = rng.standard_normal((30, 20))  # std < 20 -> treated as km (classes.py:530-531)
+    keep = topo_km.copy()
+    t = pf.TopoGrid(topo_km, 10.0, 12.0)
+    assert np.allclose(t.data, keep * 1e3)
+    # water depth from the caller's array, in its original units, mutating it (classes.py:533-536)
+    assert np.array_equal(t.water_depth, -np.minimum(keep, 0.0))
+    assert np.array_equal(topo_km, np.minimum(keep, 0.0))
+    assert pf.RhocGrid(np.full((4, 4), 2.7) + rng.standard_normal((4, 4)) * 0.01, 1, 1).data.mean() > 2000
+    assert isinstance(pf.BougGrid(data, 1, 1), pf.GravGrid) and pf.FairGrid(data, 1, 1).title == "Free-air anomaly"
+
+
+def test_nan_fill(pf, capsys):
+    data = np.arange(12.0).reshape(3, 4)
+    data[1, 1] = np.nan
+    g = pf.Grid(data, 1.0, 1.0)
+    assert np.isfinite(g.data).all() and "NaN" in capsys.readouterr().out
+
+
+def test_project_validation_messages(pf):
+    rng = np.random.default_rng(1)
+    t = pf.TopoGrid(rng.standard_normal((16, 16)) * 100 + 500, 10., 10.)
+    b = pf.BougGrid(rng.standard_normal((16, 16)) * 30, 10., 10.)
+    with pytest.raises(Exception, match="There needs to be one GravGrid object in Project"):
+        pf.Project(grids=[t, t]).init()
+    with pytest.raises(Exception, match="There needs to be one TopoGrid object in Project"):
+        pf.Project(grids=[b]).init()
+    with pytest.raises(Exception, match="Grids do not have the same shape"):
+        pf.Project(grids=[t, pf.BougGrid(np.zeros((8, 8)), 10., 10.)]).init()
+    with pytest.raises(Exception, match="same sampling intervals"):
+        pf.Project(grids=[t, pf.BougGrid(np.zeros((16, 16)), 5., 10.)]).init()
+    p = pf.Project(grids=[t, b])
+    with pytest.raises(Exception, match="Project not yet initialized - Abort"):
+        p.wlet_admit_coh()
+    with pytest.raises(Exception, match="Project not initialized. Aborting"):
+        p.estimate_cell()
+    p.init()
+    assert p.initialized and pf.cf_fl.boug == 1 and p.rhoc is None and p.zc is None
+    assert (p.nx, p.ny, p.ns) == (16, 16, t.ns) and p.water_depth is t.water_depth
+    with pytest.raises(Exception, match="'alph' should be a boolean"):
+        p.estimate_grid(alph=1)
+    with pytest.raises(Exception, match="'atype' should be one among"):
+        p.estimate_grid(atype="both")
+    with pytest.raises(Exception, match="Parallel implementation does not work"):
+        p.estimate_grid(parallel=True)
+    p2 = pf.Project(grids=[t, pf.FairGrid(np.zeros((16, 16)), 10., 10.)])
+    p2.init()
+    assert pf.cf_fl.boug == 0
+    pf.set_conf_flex()
+
+
+def test_project_container_protocol(pf):
+    g1, g2 = pf.Grid(np.zeros((4, 4)), 1, 1), pf.Grid(np.ones((4, 4)), 1, 1)
+    p = pf.Project()
+    p += g1
+    assert (p + g2).grids == [g1, g2] and list(pf.Project([g1, g2])) == [g1, g2]
+    assert p.append(g2) is p and p.extend([g1]).grids == [g1, g2, g1]
+    with pytest.raises(TypeError):
+        p.append(3)
+    with pytest.raises(TypeError):
+        p.extend([3])
+    with pytest.raises(TypeError):
+        p + 3
+    assert p.inverse == "L2" and p.mask is None and p.initialized is False
