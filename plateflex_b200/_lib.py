@@ -66,8 +66,8 @@ _SIGS = {
     "pfx_cube_xscalogram_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_cube_admit_coh_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pfx_flex_xspec_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
-    "pfx_l2_fit_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 9 + [_i, _i, _i] + [_vp] * 8, _i),
-    "pfx_l2_fit_dev": ([_i, _vp, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 9 + [_i, _i, _i] + [_vp] * 8, _i),
+    "pfx_l2_fit_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] + [_vp] * 8, _i),
+    "pfx_l2_fit_dev": ([_i, _vp, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] + [_vp] * 8, _i),
 }
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)  # AttributeError here means header and library disagree

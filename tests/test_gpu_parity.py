@@ -41,10 +41,10 @@ def test_wlet_transform_matches_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
     ref = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0, prec=64)
     assert got.shape == ref.shape == (nx, ny, 11, len(kf)) and got.dtype == np.complex128
     assert got.flags.f_contiguous
-    for s in range(len(kf)):
-        for part in (np.real, np.imag):
-            assert_maps_close(part(got[..., s]), part(ref[..., s]), f"wl_trans[{s}]",
-                              rtol=1e-9, atol_rel=1e-12 * 1e3)
+    # per scale, all 11 azimuth planes together: max|d| / max|ref| <= 1e-9 and element-wise
+    flat = lambda w: w.reshape(nx * ny * 11, len(kf), order="F")  # noqa: E731
+    for part in (np.real, np.imag):
+        assert_maps_close(part(flat(got)), part(flat(ref)), "wl_trans", rtol=1e-9, atol_rel=1e-11)
 
 
 @pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[:4])
@@ -140,8 +140,8 @@ def test_flex_model_matches_oracle(pf, ora):
             ap, cp = ora.real_xspec_functions(f["k"], *pp, conf)
             am, cm = ora.real_xspec_functions(f["k"], *pm, conf)
             da, dc = (ap - am) / (2 * h), (cp - cm) / (2 * h)
-            assert np.allclose(ja[c, j], da, rtol=2e-6, atol=1e-9 * np.abs(da).max() + 1e-300)
-            assert np.allclose(jc[c, j], dc, rtol=2e-6, atol=1e-9 * np.abs(dc).max() + 1e-300)
+            assert np.allclose(ja[c, j], da, rtol=2e-6, atol=1e-7 * np.abs(da).max() + 1e-300)
+            assert np.allclose(jc[c, j], dc, rtol=2e-6, atol=1e-7 * np.abs(dc).max() + 1e-300)
     pf.set_conf_flex()
 
 
@@ -283,6 +283,7 @@ def test_full_size_properties(pf, engine, n):
     assert np.abs(eadm).max() < 1e-10 and np.abs(ecoh).max() < 1e-10
 
 
+@pytest.mark.skipif(len(ENGINES) < 2, reason="needs both engines")
 def test_dense_and_pruned_engines_agree_at_full_size(pf, monkeypatch):
     from plateflex_b200 import _lib, classes, synthetic
     from plateflex_b200.cpwt import fused
