@@ -173,7 +173,7 @@ def clear_plans():
 
 
 def default_engine():
-    name = os.environ.get("PLATEFLEX_B200_ENGINE", "dense").lower()
+    name = os.environ.get("PLATEFLEX_B200_ENGINE", "pruned").lower()
     if name not in ("pruned", "dense"):
         raise ValueError("PLATEFLEX_B200_ENGINE must be 'pruned' or 'dense'")
     return ENGINE_DENSE if name == "dense" else ENGINE_PRUNED

@@ -21,11 +21,6 @@ void set_error(const char *fmt, ...)
     g_err = buf;
 }
 
-int plan_init_axes(pfx_plan *pl);
-int plan_init_pruned(pfx_plan *pl);
-int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);
-PlaneView pruned_view(const pfx_plan *pl, int g);
-
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -198,6 +193,7 @@ int pfx_plan_destroy(pfx_plan *pl)
     if (!pl) return PFX_OK;
     DeviceGuard guard(pl->device);
     cudaDeviceSynchronize();
+    plan_free_pruned(pl);
     if (pl->fft_fwd_ok) cufftDestroy(pl->fft_fwd);
     for (int g = 0; g < 2; g++)
         if (pl->fft_inv_ok[g]) cufftDestroy(pl->fft_inv[g]);
@@ -267,6 +263,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     const size_t nxy = (size_t)pl->nx * pl->ny;
     PFX_CHECK(forward_spectrum(pl, g1, 0));
     if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
+    if (pl->engine == PFX_ENGINE_PRUNED) PFX_CHECK(pruned_prepare(pl, ngrids));
     for (int is = is0; is < is1; is++) {
         const size_t so = (size_t)(is - is0) * nxy;
         PlaneView v1, v2;
@@ -342,6 +339,7 @@ int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, 
     PFX_CHECK(pl->scratch(2, slab * sizeof(double), (void **)&d_slab));
     PFX_CUDA(cudaMemcpyAsync(d_g, grid, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
     PFX_CHECK(forward_spectrum(pl, d_g, 0));
+    if (pl->engine == PFX_ENGINE_PRUNED) PFX_CHECK(pruned_prepare(pl, 1));
     for (int is = is0; is < is1; is++) {
         PlaneView v;
         if (pl->engine == PFX_ENGINE_DENSE) {

@@ -40,6 +40,8 @@ struct pfx_plan {
     void *d_fft_work = nullptr;
     size_t fft_work_bytes = 0;
 
+    void *pruned = nullptr;  // PrunedState of pfx_cwt_pruned.cu
+
     // grow-only scratch used by the _host entry points (inputs / outputs staging)
     void *d_scratch[8] = {};
     size_t scratch_bytes[8] = {};
@@ -62,5 +64,13 @@ int dense_scale_planes(pfx_plan *pl, int is, int ngrids);
 PlaneView dense_view(const pfx_plan *pl, int g);
 
 int plan_init_dense(pfx_plan *pl);
+int plan_init_axes(pfx_plan *pl);
+
+// Pruned engine (pfx_cwt_pruned.cu)
+int plan_init_pruned(pfx_plan *pl);
+void plan_free_pruned(pfx_plan *pl);
+int pruned_prepare(pfx_plan *pl, int ngrids);          // admissibility transform Z, once per set of spectra
+int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);  // -> compact W planes of scale `is`
+PlaneView pruned_view(const pfx_plan *pl, int g);
 
 }  // namespace pfx

@@ -10,7 +10,7 @@ from helpers import A_TOL, CHI2_RTOL, F_TOL, STD_RTOL, TE_TOL, assert_maps_close
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-ENGINES = ["dense"]
+ENGINES = ["dense", "pruned"]
 
 
 @pytest.fixture(params=ENGINES)
