@@ -23,6 +23,7 @@
 // words in every radix stage and the final stage leaves the line in output order.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "pfx_plan.hpp"
 
@@ -189,27 +190,27 @@ __device__ __forceinline__ void fft_first_stage(double2 *sm, const Load &load, c
     }
 }
 
-template <class Load>
+// MAXLR = log2 of the largest radix compiled in: 4 (radix 16, ~150 registers) or 3 (radix 8, more
+// stages but twice the resident warps).
+template <int MAXLR, class Load>
 __device__ __forceinline__ void fft_lines(double2 *sm, const Load &load, const AxisDesc &A, int cpc, int plane, int lo,
                                           int K, int rho0, const double2 *__restrict__ tw,
                                           const double2 *__restrict__ root)
 {
-    switch (A.lrad[0]) {
-        case 1: fft_first_stage<1>(sm, load, A, cpc, plane, lo, K, rho0, tw); break;
-        case 2: fft_first_stage<2>(sm, load, A, cpc, plane, lo, K, rho0, tw); break;
-        case 3: fft_first_stage<3>(sm, load, A, cpc, plane, lo, K, rho0, tw); break;
-        default: fft_first_stage<4>(sm, load, A, cpc, plane, lo, K, rho0, tw); break;
-    }
-    int logM = A.lrad[0];
+    const int l0 = A.lrad[0];
+    if (MAXLR >= 4 && l0 == 4) fft_first_stage<(MAXLR >= 4 ? 4 : 3)>(sm, load, A, cpc, plane, lo, K, rho0, tw);
+    else if (l0 == 3) fft_first_stage<3>(sm, load, A, cpc, plane, lo, K, rho0, tw);
+    else if (l0 == 2) fft_first_stage<2>(sm, load, A, cpc, plane, lo, K, rho0, tw);
+    else fft_first_stage<1>(sm, load, A, cpc, plane, lo, K, rho0, tw);
+    int logM = l0;
     for (int s = 1; s < A.nstages; s++) {
         __syncthreads();
-        switch (A.lrad[s]) {
-            case 1: fft_stage<1>(sm, A, cpc, plane, logM, root); break;
-            case 2: fft_stage<2>(sm, A, cpc, plane, logM, root); break;
-            case 3: fft_stage<3>(sm, A, cpc, plane, logM, root); break;
-            default: fft_stage<4>(sm, A, cpc, plane, logM, root); break;
-        }
-        logM += A.lrad[s];
+        const int l = A.lrad[s];
+        if (MAXLR >= 4 && l == 4) fft_stage<(MAXLR >= 4 ? 4 : 3)>(sm, A, cpc, plane, logM, root);
+        else if (l == 3) fft_stage<3>(sm, A, cpc, plane, logM, root);
+        else if (l == 2) fft_stage<2>(sm, A, cpc, plane, logM, root);
+        else fft_stage<1>(sm, A, cpc, plane, logM, root);
+        logM += l;
     }
     __syncthreads();
 }
@@ -228,7 +229,8 @@ struct PrunedArgs {
 
 // Pass 1: for transform t = blockIdx.y and spectrum column a = alo + m (m = blockIdx.x): the
 // y-direction transform of v1(b)*X[b][a] over the support rows, outputs j < ny, times (c/P)*u1(a).
-__global__ void __launch_bounds__(NT) pruned_pass1_kernel(PrunedArgs a)
+template <int MAXLR>
+__global__ void __launch_bounds__(NT, (MAXLR >= 4 ? 1 : 3)) pruned_pass1_kernel(PrunedArgs a)
 {
     extern __shared__ double2 smem[];
     const ScaleDesc &sd = a.sd;
@@ -261,9 +263,9 @@ __global__ void __launch_bounds__(NT) pruned_pass1_kernel(PrunedArgs a)
     for (int part = 0; part < nsplit; part++) {
         const int rho0 = part << A.logrc;
         if (staged)
-            fft_lines(sm, from_smem, A, 1, plane, lo, K, rho0, tw, a.rooty);
+            fft_lines<MAXLR>(sm, from_smem, A, 1, plane, lo, K, rho0, tw, a.rooty);
         else
-            fft_lines(sm, from_global, A, 1, plane, lo, K, rho0, tw, a.rooty);
+            fft_lines<MAXLR>(sm, from_global, A, 1, plane, lo, K, rho0, tw, a.rooty);
         // outputs j = q*r + rho0 + rho, j < ny
         const int nq = (A.nout + A.r - 1) >> A.logr;
         for (int o = threadIdx.x; o < (nq << A.logrc); o += NT) {
@@ -280,8 +282,8 @@ __global__ void __launch_bounds__(NT) pruned_pass1_kernel(PrunedArgs a)
 
 // Pass 2: for transform t = blockIdx.y and output rows j0 .. j0+cpc-1: the x-direction transform
 // of T[t][:, j], outputs i < nx, minus c*E*Z (the admissibility term), into W[t][j][i].
-template <int CPC>
-__global__ void __launch_bounds__(NT) pruned_pass2_kernel(PrunedArgs a)
+template <int CPC, int MAXLR>
+__global__ void __launch_bounds__(NT, (MAXLR >= 4 ? 1 : 3)) pruned_pass2_kernel(PrunedArgs a)
 {
     extern __shared__ double2 smem[];
     const ScaleDesc &sd = a.sd;
@@ -312,9 +314,9 @@ __global__ void __launch_bounds__(NT) pruned_pass2_kernel(PrunedArgs a)
     for (int part = 0; part < nsplit; part++) {
         const int rho0 = part << A.logrc;
         if (staged)
-            fft_lines(sm, from_smem, A, CPC, plane, lo, K, rho0, tw, a.rootx);
+            fft_lines<MAXLR>(sm, from_smem, A, CPC, plane, lo, K, rho0, tw, a.rootx);
         else
-            fft_lines(sm, from_global, A, CPC, plane, lo, K, rho0, tw, a.rootx);
+            fft_lines<MAXLR>(sm, from_global, A, CPC, plane, lo, K, rho0, tw, a.rootx);
         const int nq = (A.nout + A.r - 1) >> A.logr;
         const int per = nq << A.logrc;
         for (int o = threadIdx.x; o < per * CPC; o += NT) {
@@ -405,7 +407,7 @@ int ilog2(int v)
     return l;
 }
 
-void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_elems, int cpc)
+void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_elems, int cpc, int maxlr)
 {
     A.N = N;
     A.logN = ilog2(N);
@@ -421,10 +423,14 @@ void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_elems, in
     int rem = A.logL, n = 0;
     int tmp[MAX_STAGES];
     while (rem > 0) {
-        int lr = rem >= 4 ? 4 : rem;
-        if (rem == 5) lr = 3;        // 32 = 8 * 4
-        if (rem == 6) lr = 3;        // 64 = 8 * 8
-        if (rem == 9) lr = 3;        // 512 = 8 * 8 * 8
+        int lr = rem >= maxlr ? maxlr : rem;
+        if (maxlr == 4) {
+            if (rem == 5) lr = 3;    // 32 = 8 * 4
+            if (rem == 6) lr = 3;    // 64 = 8 * 8
+            if (rem == 9) lr = 3;    // 512 = 8 * 8 * 8
+        } else if (rem == 4) {
+            lr = 2;                  // 16 = 4 * 4
+        }
         tmp[n++] = lr;
         rem -= lr;
     }
@@ -456,6 +462,7 @@ struct PrunedState {
     bool fft_z_ok[2] = {false, false};
     size_t smem1 = 0, smem2 = 0;
     int cpc = 2;
+    int maxlr = 3;
     std::vector<std::pair<void *, size_t>> owned;
 };
 
@@ -490,6 +497,10 @@ int plan_init_pruned(pfx_plan *pl)
     const size_t budget = (size_t)dev_smem / sizeof(double2);
 
     st->cpc = (NX <= 4096) ? 2 : 1;
+    {
+        const char *e = getenv("PLATEFLEX_B200_RADIX");
+        st->maxlr = (e && atoi(e) == 16) ? 4 : 3;
+    }
     st->sd.resize(ns);
     size_t tabu_n = 0, tabv_n = 0, twa_n = 0, twb_n = 0, kamax_all = 0;
     std::vector<int> h_lo((size_t)ns * 4 * PFX_NA);
@@ -512,8 +523,8 @@ int plan_init_pruned(pfx_plan *pl)
             kbmax = std::max(kbmax, sd.kb[ia]);
             sd.ce[ia] = c.norm * c.e0[ia];
         }
-        plan_axis(sd.ax, NX, std::max(kamax, 1), nx, budget, st->cpc);
-        plan_axis(sd.ay, NY, std::max(kbmax, 1), ny, budget, 1);
+        plan_axis(sd.ax, NX, std::max(kamax, 1), nx, budget, st->cpc, st->maxlr);
+        plan_axis(sd.ay, NY, std::max(kbmax, 1), ny, budget, 1, st->maxlr);
         sd.kamax = std::max(kamax, 1);
         sd.tabu = tabu_n;
         sd.tabv = tabv_n;
@@ -605,9 +616,12 @@ int plan_init_pruned(pfx_plan *pl)
     }
     for (int g = 0; g < 2; g++) PFX_CUFFT(cufftSetWorkArea(st->fft_z[g], pl->d_fft_work));
 
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem1));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem1));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem1));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
+    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
     return PFX_OK;
 }
 
@@ -674,12 +688,20 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     const size_t sm1 = (plane(sd.ay) + (sd.ay.r > 1 ? sd.ay.L : 0)) * sizeof(double2);
     const size_t sm2 = (plane(sd.ax) + (sd.ax.r > 1 ? sd.ax.L : 0)) * st->cpc * sizeof(double2);
     dim3 g1(sd.kamax, PFX_NA * ngrids);
-    pruned_pass1_kernel<<<g1, NT, sm1, pl->stream>>>(a);
     dim3 g2((pl->ny + st->cpc - 1) / st->cpc, PFX_NA * ngrids);
-    if (st->cpc == 2)
-        pruned_pass2_kernel<2><<<g2, NT, sm2, pl->stream>>>(a);
-    else
-        pruned_pass2_kernel<1><<<g2, NT, sm2, pl->stream>>>(a);
+    if (st->maxlr >= 4) {
+        pruned_pass1_kernel<4><<<g1, NT, sm1, pl->stream>>>(a);
+        if (st->cpc == 2)
+            pruned_pass2_kernel<2, 4><<<g2, NT, sm2, pl->stream>>>(a);
+        else
+            pruned_pass2_kernel<1, 4><<<g2, NT, sm2, pl->stream>>>(a);
+    } else {
+        pruned_pass1_kernel<3><<<g1, NT, sm1, pl->stream>>>(a);
+        if (st->cpc == 2)
+            pruned_pass2_kernel<2, 3><<<g2, NT, sm2, pl->stream>>>(a);
+        else
+            pruned_pass2_kernel<1, 3><<<g2, NT, sm2, pl->stream>>>(a);
+    }
     PFX_CUDA(cudaGetLastError());
     pl->launches += 2;
     return PFX_OK;
