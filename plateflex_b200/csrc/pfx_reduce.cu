@@ -109,9 +109,15 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
     eco = jk_spread(co2);
 }
 
-__device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int j)
+__device__ __forceinline__ double2 load_z(const PlaneView &v, int i, int j)
+{
+    return v.zc ? __ldg(v.zc + (size_t)j * v.ld + i) : make_double2(0.0, 0.0);
+}
+
+__device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int j, double2 z)
 {
     const double2 w = __ldg(v.base + (size_t)p * v.plane_stride + (size_t)(j + v.off_j) * v.ld + (i + v.off_i));
+    if (v.zc) return make_double2(w.x - v.ce[p] * z.x, w.y - v.ce[p] * z.y);
     return make_double2(w.x * v.scale, w.y * v.scale);
 }
 
@@ -124,13 +130,15 @@ __global__ void __launch_bounds__(128)
     const int j = blockIdx.y;
     if (i >= nx) return;
     const size_t o = (size_t)j * nx + i;
+    const double2 z1 = load_z(w1, i, j);
+    const double2 z2 = (MODE == RED_SCALOGRAM) ? z1 : load_z(w2, i, j);
 
     if (MODE == RED_SCALOGRAM) {
         double s[NA];
         double tot = 0.0;
 #pragma unroll
         for (int a = 0; a < NA; a++) {
-            const double2 w = load_w(w1, a, i, j);
+            const double2 w = load_w(w1, a, i, j, z1);
             s[a] = fabs(w.x * w.x + w.y * w.y);  // CABS(w*CONJG(w)), cpwt.f90:224
             tot += s[a];
         }
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(128)
         double tr = 0.0, ti = 0.0;
 #pragma unroll
         for (int a = 0; a < NA; a++) {
-            const double2 u = load_w(w1, a, i, j), v = load_w(w2, a, i, j);
+            const double2 u = load_w(w1, a, i, j, z1), v = load_w(w2, a, i, j, z2);
             xr[a] = u.x * v.x + u.y * v.y;  // w1*CONJG(w2), cpwt.f90:274
             xi[a] = u.y * v.x - u.x * v.y;
             tr += xr[a];
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(128)
         double t1 = 0.0, t2 = 0.0, tx = 0.0;
 #pragma unroll
         for (int a = 0; a < NA; a++) {
-            const double2 u = load_w(w1, a, i, j), v = load_w(w2, a, i, j);
+            const double2 u = load_w(w1, a, i, j, z1), v = load_w(w2, a, i, j, z2);
             s1[a] = fabs(u.x * u.x + u.y * u.y);  // cpwt.f90:333
             s2[a] = fabs(v.x * v.x + v.y * v.y);  // cpwt.f90:334
             xr[a] = u.x * v.x + u.y * v.y;        // Re(w1*CONJG(w2)), cpwt.f90:335
@@ -181,7 +189,7 @@ __global__ void crop_kernel(int nx, int ny, PlaneView w, double2 *__restrict__ s
     const int j = blockIdx.y;
     const int p = blockIdx.z;
     if (i >= nx) return;
-    slab[((size_t)p * ny + j) * nx + i] = load_w(w, p, i, j);
+    slab[((size_t)p * ny + j) * nx + i] = load_w(w, p, i, j, load_z(w, i, j));
 }
 
 }  // namespace
