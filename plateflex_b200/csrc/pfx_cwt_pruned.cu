@@ -26,382 +26,11 @@
 #include <cstdlib>
 
 #include "pfx_plan.hpp"
+#include "pfx_pruned.hpp"
 
 namespace pfx {
 
 namespace {
-
-constexpr int MAX_STAGES = 6;
-constexpr int NT = 256;  // threads per CTA
-
-struct AxisDesc {
-    int N, logN;       // padded length of the axis
-    int L, logL;       // FFT length (power of two >= support width)
-    int r, logr;       // residues per line, N / L
-    int rc, logrc;     // residues handled by one CTA (r / rsplit)
-    int nout;          // outputs needed along this axis (nx or ny)
-    int nstages;
-    int lrad[MAX_STAGES];  // log2 of the radix of each stage, first executed first
-    int padshift;          // element padding e + (e >> padshift) when rc < 8 (31 = none)
-    int stw_off[MAX_STAGES];  // offset of each stage's twiddles in the shared-memory table
-    int stw_total;
-};
-
-struct ScaleDesc {
-    AxisDesc ax, ay;
-    int alo[PFX_NA], ka[PFX_NA];  // support [alo, alo+ka) along x per azimuth (signed wavenumber index)
-    int blo[PFX_NA], kb[PFX_NA];
-    double ce[PFX_NA];            // norm * exp(-0.5*(kx0^2+ky0^2)): factor of the Z correction
-    int kamax;                    // rows of T per transform
-    size_t tabu, tabv;            // offsets (doubles) of the weight tables of this scale
-    size_t twa, twb;              // offsets (double2) of the stage-1 twiddle tables
-};
-
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b)
-{
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// exp(+2 pi i k / 16), k = 0..7
-__device__ __forceinline__ double2 w16(int k)
-{
-    constexpr double C1 = 0.92387953251128673848, S1 = 0.38268343236508978178, H = 0.70710678118654752440;
-    switch (k) {
-        case 0: return make_double2(1., 0.);
-        case 1: return make_double2(C1, S1);
-        case 2: return make_double2(H, H);
-        case 3: return make_double2(S1, C1);
-        case 4: return make_double2(0., 1.);
-        case 5: return make_double2(-S1, C1);
-        case 6: return make_double2(-H, H);
-        default: return make_double2(-C1, S1);
-    }
-}
-
-// In-register inverse DFT (exp(+i...)) of R = 2,4,8,16 points, natural order in and out.
-template <int R>
-__device__ __forceinline__ void dft(double2 (&v)[R])
-{
-    if constexpr (R == 2) {
-        const double2 a = v[0], b = v[1];
-        v[0] = cadd(a, b);
-        v[1] = csub(a, b);
-    } else {
-        double2 e[R / 2], o[R / 2];
-#pragma unroll
-        for (int k = 0; k < R / 2; k++) {
-            e[k] = v[2 * k];
-            o[k] = v[2 * k + 1];
-        }
-        dft<R / 2>(e);
-        dft<R / 2>(o);
-#pragma unroll
-        for (int k = 0; k < R / 2; k++) {
-            double2 t;
-            const int k16 = k * (16 / R);
-            if (k16 == 0) {
-                t = o[k];
-            } else if (k16 == 4) {
-                t = make_double2(-o[k].y, o[k].x);  // * i
-            } else if (k16 == 2) {
-                constexpr double H = 0.70710678118654752440;
-                t = make_double2(H * (o[k].x - o[k].y), H * (o[k].x + o[k].y));
-            } else if (k16 == 6) {
-                constexpr double H = 0.70710678118654752440;
-                t = make_double2(-H * (o[k].x + o[k].y), H * (o[k].x - o[k].y));
-            } else {
-                t = cmul(o[k], w16(k16));
-            }
-            v[k] = cadd(e[k], t);
-            v[k + R / 2] = csub(e[k], t);
-        }
-    }
-}
-
-__device__ __forceinline__ int padded(int e, int padshift) { return e + (e >> padshift); }
-
-// Shared-memory tables of one CTA: stage twiddles w_{M*R}^{q0} for every stage after the first, and
-// the per-residue factors of the first-stage twiddle recurrence.
-struct SmemTables {
-    const double2 *stw;  // stage s (>= 1) at stw + A.stw_off[s], M_s entries
-    const double2 *g;    // [rc]  w_N^{(L/R1)(rho+1)}: step between the R1 inputs of a first-stage butterfly
-    const double2 *h;    // [rc]  w_N^{-L(rho+1)}: correction when the support index wraps modulo L
-};
-
-__device__ __forceinline__ void load_stage_twiddles(double2 *stw, const AxisDesc &A, const double2 *__restrict__ root)
-{
-    int logM = A.lrad[0];
-    for (int s = 1; s < A.nstages; s++) {
-        const int rs = A.logN - (logM + A.lrad[s]);
-        for (int q0 = threadIdx.x; q0 < (1 << logM); q0 += NT) stw[A.stw_off[s] + q0] = __ldg(root + (q0 << rs));
-        logM += A.lrad[s];
-    }
-}
-
-__device__ __forceinline__ void load_residue_factors(double2 *gt, double2 *ht, const AxisDesc &A, int rho0,
-                                                     const double2 *__restrict__ root)
-{
-    for (int rho = threadIdx.x; rho < A.rc; rho += NT) {
-        const int e = rho0 + rho + 1;
-        gt[rho] = __ldg(root + ((e << (A.logL - A.lrad[0])) & (A.N - 1)));
-        ht[rho] = __ldg(root + ((A.N - ((e << A.logL) & (A.N - 1))) & (A.N - 1)));
-    }
-}
-
-// One radix-R stage (not the first) over the interleaved FFTs of all `cpc` lines held by the CTA.
-//   sub-FFT size M = 2^logM, block size M*R; twiddle for input k at offset q0: (w_{M*R}^{q0})^k
-template <int LR>
-__device__ __forceinline__ void fft_stage(double2 *sm, const AxisDesc &A, int cpc, int plane, int logM,
-                                          const double2 *stw)
-{
-    constexpr int R = 1 << LR;
-    const int logbf = A.logL - LR;  // butterflies per FFT
-    const int total = cpc << (logbf + A.logrc);
-    for (int w = threadIdx.x; w < total; w += NT) {
-        const int rho = w & (A.rc - 1);
-        const int u = (w >> A.logrc) & ((1 << logbf) - 1);
-        const int c = w >> (A.logrc + logbf);
-        const int q0 = u & ((1 << logM) - 1);
-        const int base = ((u >> logM) << (logM + LR)) + q0;
-        double2 *p = sm + c * plane + rho;
-        double2 v[R];
-#pragma unroll
-        for (int k = 0; k < R; k++) v[k] = p[padded(base + (k << logM), A.padshift) << A.logrc];
-        if (q0 != 0) {
-            const double2 w1 = stw[q0];
-            double2 t = w1;
-            v[1] = cmul(v[1], t);
-#pragma unroll
-            for (int k = 2; k < R; k++) {
-                t = cmul(t, w1);
-                v[k] = cmul(v[k], t);
-            }
-        }
-        dft<R>(v);
-#pragma unroll
-        for (int k = 0; k < R; k++) p[padded(base + (k << logM), A.padshift) << A.logrc] = v[k];
-    }
-}
-
-// First stage fused with the input twiddles.  load(c, m) returns the weighted input m = a - lo of
-// line c (from the staged copy in shared memory, or straight from global memory when r == 1 and every
-// input is used exactly once).  The twiddle of input k of a butterfly is exp(2 pi i a_k (rho+1)/N) with
-// a_k = lo + ((n_k - lo) mod L), n_k = nlow + k*L/R: one table read tw[nlow*r + rho] for k = 0, then
-// t_k = t_{k-1} * g[rho], times h[rho] once when the support index wraps.
-template <int LR, class Load>
-__device__ __forceinline__ void fft_first_stage(double2 *sm, const Load &load, const AxisDesc &A, int cpc, int plane,
-                                                int lo, int K, int rho0, const double2 *__restrict__ tw,
-                                                const SmemTables &tb)
-{
-    constexpr int R = 1 << LR;
-    const int logbf = A.logL - LR;
-    const int total = 1 << (logbf + A.logrc);
-    const int step = 1 << logbf;
-    for (int w = threadIdx.x; w < total; w += NT) {
-        const int rho = w & (A.rc - 1);
-        const int u = w >> A.logrc;
-        // natural index of the butterfly's first input: digits of u re-assembled in reverse order
-        int nlow = 0, rest = u;
-        for (int s = 1; s < A.nstages; s++) {
-            const int d = rest & ((1 << A.lrad[s]) - 1);
-            rest >>= A.lrad[s];
-            nlow = (nlow << A.lrad[s]) | d;
-        }
-        const int m0 = (nlow - lo) & (A.L - 1);
-        const double2 t0 = __ldg(tw + ((size_t)nlow << A.logr) + rho0 + rho);
-        const double2 g = tb.g[rho], h = tb.h[rho];
-        for (int c = 0; c < cpc; c++) {
-            double2 v[R];
-#pragma unroll
-            for (int k = 0; k < R; k++) {
-                const int m = (m0 + k * step) & (A.L - 1);
-                v[k] = (m < K) ? load(c, m) : make_double2(0., 0.);
-            }
-            double2 t = t0;
-            v[0] = cmul(v[0], t);
-#pragma unroll
-            for (int k = 1; k < R; k++) {
-                t = cmul(t, g);
-                if (((m0 + k * step) & (A.L - 1)) < step) t = cmul(t, h);  // wrapped between k-1 and k
-                v[k] = cmul(v[k], t);
-            }
-            dft<R>(v);
-            double2 *p = sm + c * plane + rho;
-#pragma unroll
-            for (int k = 0; k < R; k++) p[padded((u << LR) + k, A.padshift) << A.logrc] = v[k];
-        }
-    }
-}
-
-// MAXLR = log2 of the largest radix compiled in: 4 (radix 16, ~150 registers) or 3 (radix 8, more
-// stages but three resident CTAs per SM).
-template <int MAXLR, class Load>
-__device__ __forceinline__ void fft_lines(double2 *sm, const Load &load, const AxisDesc &A, int cpc, int plane, int lo,
-                                          int K, int rho0, const double2 *__restrict__ tw, const SmemTables &tb)
-{
-    const int l0 = A.lrad[0];
-    if (MAXLR >= 4 && l0 == 4) fft_first_stage<(MAXLR >= 4 ? 4 : 3)>(sm, load, A, cpc, plane, lo, K, rho0, tw, tb);
-    else if (l0 == 3) fft_first_stage<3>(sm, load, A, cpc, plane, lo, K, rho0, tw, tb);
-    else if (l0 == 2) fft_first_stage<2>(sm, load, A, cpc, plane, lo, K, rho0, tw, tb);
-    else fft_first_stage<1>(sm, load, A, cpc, plane, lo, K, rho0, tw, tb);
-    int logM = l0;
-    for (int s = 1; s < A.nstages; s++) {
-        __syncthreads();
-        const int l = A.lrad[s];
-        const double2 *stw = tb.stw + A.stw_off[s];
-        if (MAXLR >= 4 && l == 4) fft_stage<(MAXLR >= 4 ? 4 : 3)>(sm, A, cpc, plane, logM, stw);
-        else if (l == 3) fft_stage<3>(sm, A, cpc, plane, logM, stw);
-        else if (l == 2) fft_stage<2>(sm, A, cpc, plane, logM, stw);
-        else fft_stage<1>(sm, A, cpc, plane, logM, stw);
-        logM += l;
-    }
-    __syncthreads();
-}
-
-struct PrunedArgs {
-    ScaleDesc sd;
-    int nx, ny, NX, NY, ngrids;
-    const double2 *spec0, *spec1;  // padded spectra [b][a]
-    const double *tabu, *tabv;     // weight tables (all scales)
-    const double2 *twa, *twb;      // stage-1 twiddle tables (all scales)
-    const double2 *rootx, *rooty;  // exp(2 pi i m / N)
-    double2 *T;                    // [t][ka row][j]  intermediate, t = ia + 11*g
-    double2 *W;                    // [t][j][i] output planes (main Gaussian term only)
-};
-
-// shared memory carve-up, in double2 elements: [data][staged inputs][stage twiddles][g][h]
-__device__ __forceinline__ void carve(double2 *smem, const AxisDesc &A, int cpc, int plane, double2 *&y, double2 *&stw,
-                                      double2 *&gt, double2 *&ht)
-{
-    y = smem + cpc * plane;
-    stw = y + ((A.r > 1) ? cpc * A.L : 0);
-    gt = stw + A.stw_total;
-    ht = gt + A.rc;
-}
-
-// Pass 1: for transform t = blockIdx.y and spectrum columns a = alo + m (m = blockIdx.x, + gridDim.x, ..):
-// the y-direction transform of v1(b)*X[b][a] over the support rows, outputs j < ny, times (c/P)*u1(a).
-template <int MAXLR>
-__global__ void __launch_bounds__(NT, (MAXLR >= 4 ? 1 : 3)) pruned_pass1_kernel(PrunedArgs a)
-{
-    extern __shared__ double2 smem[];
-    const ScaleDesc &sd = a.sd;
-    const AxisDesc &A = sd.ay;
-    const int t = blockIdx.y, ia = t % PFX_NA, g = t / PFX_NA;
-    if ((int)blockIdx.x >= sd.ka[ia]) return;
-    const int K = sd.kb[ia], lo = sd.blo[ia];
-    const int plane = (padded(A.L - 1, A.padshift) + 1) << A.logrc;
-    double2 *sm = smem, *y, *stw, *gt, *ht;
-    carve(smem, A, 1, plane, y, stw, gt, ht);
-    load_stage_twiddles(stw, A, a.rooty);
-    const int nsplit = A.r >> A.logrc;
-    if (nsplit == 1) load_residue_factors(gt, ht, A, 0, a.rooty);
-    const SmemTables tb{stw, gt, ht};
-    const double2 *spec = g ? a.spec1 : a.spec0;
-    const double *tv = a.tabv + sd.tabv + (size_t)ia * A.L;
-    const double2 *tw = a.twb + sd.twb + ((size_t)ia << A.logN);
-    const int NXl = a.NX, NYm = a.NY - 1;
-    const bool staged = A.r > 1;
-    for (int m = blockIdx.x; m < sd.ka[ia]; m += gridDim.x) {
-        const int acol = (sd.alo[ia] + m) & (a.NX - 1);
-        auto from_global = [&](int, int mb) {
-            const double2 x = __ldg(spec + (size_t)((lo + mb) & NYm) * NXl + acol);
-            const double wv = tv[mb];
-            return make_double2(x.x * wv, x.y * wv);
-        };
-        auto from_smem = [&](int, int mb) { return y[mb]; };
-        if (staged)
-            for (int mb = threadIdx.x; mb < K; mb += NT) y[mb] = from_global(0, mb);
-        __syncthreads();
-        const double wu = a.tabu[sd.tabu + (size_t)ia * sd.ax.L + m];
-        double2 *Trow = a.T + ((size_t)t * sd.kamax + m) * a.ny;
-        for (int part = 0; part < nsplit; part++) {
-            const int rho0 = part << A.logrc;
-            if (nsplit > 1) {
-                load_residue_factors(gt, ht, A, rho0, a.rooty);
-                __syncthreads();
-            }
-            if (staged)
-                fft_lines<MAXLR>(sm, from_smem, A, 1, plane, lo, K, rho0, tw, tb);
-            else
-                fft_lines<MAXLR>(sm, from_global, A, 1, plane, lo, K, rho0, tw, tb);
-            // outputs j = q*r + rho0 + rho, j < ny
-            const int nq = (A.nout + A.r - 1) >> A.logr;
-            for (int o = threadIdx.x; o < (nq << A.logrc); o += NT) {
-                const int rho = o & (A.rc - 1), q = o >> A.logrc;
-                const int j = (q << A.logr) + rho0 + rho;
-                if (j < A.nout) {
-                    const double2 v = sm[(padded(q, A.padshift) << A.logrc) + rho];
-                    Trow[j] = make_double2(v.x * wu, v.y * wu);
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// Pass 2: for transform t = blockIdx.y and output rows j0 .. j0+CPC-1 (row groups blockIdx.x, + gridDim.x,
-// ..): the x-direction transform of T[t][:, j], outputs i < nx, into W[t][j][i].  The admissibility
-// correction -c*E*Z is applied by the consumers of W (PlaneView::zc).
-template <int CPC, int MAXLR>
-__global__ void __launch_bounds__(NT, (MAXLR >= 4 ? 1 : 3)) pruned_pass2_kernel(PrunedArgs a)
-{
-    extern __shared__ double2 smem[];
-    const ScaleDesc &sd = a.sd;
-    const AxisDesc &A = sd.ax;
-    const int t = blockIdx.y, ia = t % PFX_NA;
-    const int K = sd.ka[ia], lo = sd.alo[ia];
-    const int plane = (padded(A.L - 1, A.padshift) + 1) << A.logrc;
-    double2 *sm = smem, *y, *stw, *gt, *ht;
-    carve(smem, A, CPC, plane, y, stw, gt, ht);
-    load_stage_twiddles(stw, A, a.rootx);
-    const int nsplit = A.r >> A.logrc;
-    if (nsplit == 1) load_residue_factors(gt, ht, A, 0, a.rootx);
-    const SmemTables tb{stw, gt, ht};
-    const double2 *Tt = a.T + (size_t)t * sd.kamax * a.ny;
-    const double2 *tw = a.twa + sd.twa + ((size_t)ia << A.logN);
-    const int nyl = a.ny, Ll = A.L;
-    const bool staged = A.r > 1;
-    const int ngroups = (a.ny + CPC - 1) / CPC;
-    for (int cg = blockIdx.x; cg < ngroups; cg += gridDim.x) {
-        const int j0 = cg * CPC;
-        auto from_global = [&](int c, int m) {
-            const int j = j0 + c;
-            return (j < nyl) ? __ldg(Tt + (size_t)m * nyl + j) : make_double2(0., 0.);
-        };
-        auto from_smem = [&](int c, int m) { return y[c * Ll + m]; };
-        if (staged)
-            for (int o = threadIdx.x; o < K * CPC; o += NT) {
-                const int c = o % CPC, m = o / CPC;
-                y[c * Ll + m] = from_global(c, m);
-            }
-        __syncthreads();
-        for (int part = 0; part < nsplit; part++) {
-            const int rho0 = part << A.logrc;
-            if (nsplit > 1) {
-                load_residue_factors(gt, ht, A, rho0, a.rootx);
-                __syncthreads();
-            }
-            if (staged)
-                fft_lines<MAXLR>(sm, from_smem, A, CPC, plane, lo, K, rho0, tw, tb);
-            else
-                fft_lines<MAXLR>(sm, from_global, A, CPC, plane, lo, K, rho0, tw, tb);
-            const int nq = (A.nout + A.r - 1) >> A.logr;
-            const int per = nq << A.logrc;
-            for (int o = threadIdx.x; o < per * CPC; o += NT) {
-                const int c = o / per, oo = o - c * per;
-                const int rho = oo & (A.rc - 1), q = oo >> A.logrc;
-                const int i = (q << A.logr) + rho0 + rho;
-                const int j = j0 + c;
-                if (i < A.nout && j < a.ny)
-                    a.W[((size_t)t * a.ny + j) * a.nx + i] = sm[c * plane + (padded(q, A.padshift) << A.logrc) + rho];
-            }
-            __syncthreads();
-        }
-    }
-}
 
 // ---- table builders ------------------------------------------------------------------------
 __global__ void root_kernel(int N, double2 *root)
@@ -468,12 +97,6 @@ __global__ void zcrop_kernel(int nx, int ny, int NX, size_t P, double scale, con
     zc[((size_t)g * ny + j) * nx + i] = make_double2(v.x * scale, v.y * scale);
 }
 
-size_t smem_bytes(const AxisDesc &A, int cpc)
-{
-    const size_t plane = (size_t)((A.L - 1) + ((A.L - 1) >> A.padshift) + 1) * A.rc;
-    return (plane * cpc + (A.r > 1 ? (size_t)A.L * cpc : 0) + A.stw_total + 2 * (size_t)A.rc) * sizeof(double2);
-}
-
 int ilog2(int v)
 {
     int l = 0;
@@ -481,7 +104,8 @@ int ilog2(int v)
     return l;
 }
 
-void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_elems, int cpc, int maxlr)
+// Choose the FFT length of an axis for a support of K samples and fit the line in shared memory.
+void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_bytes, int cpc)
 {
     A.N = N;
     A.logN = ilog2(N);
@@ -493,46 +117,14 @@ void plan_axis(AxisDesc &A, int N, int K, int nout, size_t smem_budget_elems, in
     A.r = N / L;
     A.logr = A.logN - A.logL;
     A.nout = nout;
-    // radix plan: as many radix-16 stages as possible, remainder 8 / 4 / 2, largest radix first
-    int rem = A.logL, n = 0;
-    int tmp[MAX_STAGES];
-    while (rem > 0) {
-        int lr = rem >= maxlr ? maxlr : rem;
-        if (maxlr == 4) {
-            if (rem == 5) lr = 3;    // 32 = 8 * 4
-            if (rem == 6) lr = 3;    // 64 = 8 * 8
-            if (rem == 9) lr = 3;    // 512 = 8 * 8 * 8
-        } else if (rem == 4) {
-            lr = 2;                  // 16 = 4 * 4
-        }
-        tmp[n++] = lr;
-        rem -= lr;
-    }
-    A.nstages = n;
-    for (int s = 0; s < n; s++) A.lrad[s] = tmp[s];
-    for (int s = n; s < MAX_STAGES; s++) A.lrad[s] = 0;
-    // residues per CTA: all of them unless the line does not fit in shared memory
     A.rc = A.r;
     A.logrc = A.logr;
-    auto plane_elems = [&](int rc, int padshift) { return (size_t)((L - 1) + ((L - 1) >> padshift) + 1) * rc; };
-    A.padshift = (A.rc >= 8) ? 31 : 3;
-    {
-        int logM = A.lrad[0], off = 0;
-        A.stw_off[0] = 0;
-        for (int st = 1; st < MAX_STAGES; st++) {
-            A.stw_off[st] = off;
-            if (st < A.nstages) {
-                off += 1 << logM;
-                logM += A.lrad[st];
-            }
-        }
-        A.stw_total = off;
-    }
-    const size_t ystage = ((A.r > 1) ? (size_t)L * cpc : 0) + A.stw_total + 2 * (size_t)A.r;
-    while (A.rc > 1 && plane_elems(A.rc, A.padshift) * cpc + ystage > smem_budget_elems) {
+    A.pad = (A.rc < 8 && A.logL >= 8) ? 1 : 0;
+    // residues per pass over shared memory: all of them unless the line does not fit
+    while (A.rc > 1 && prn_smem_bytes(A, cpc) > smem_budget_bytes) {
         A.rc /= 2;
         A.logrc--;
-        A.padshift = (A.rc >= 8) ? 31 : 3;
+        A.pad = (A.rc < 8 && A.logL >= 8) ? 1 : 0;
     }
 }
 
@@ -548,8 +140,7 @@ struct PrunedState {
     bool fft_z_ok[2] = {false, false};
     size_t smem1 = 0, smem2 = 0;
     int cpc = 2;
-    int maxlr = 3;
-    int ctas_per_transform = 64;
+    int ctas_per_transform = 128;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
     std::vector<std::pair<void *, size_t>> owned;
 };
@@ -582,12 +173,10 @@ int plan_init_pruned(pfx_plan *pl)
     const size_t P = (size_t)NX * NY;
     int dev_smem = 0;
     PFX_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->device));
-    const size_t budget = (size_t)dev_smem / sizeof(double2);
+    const size_t budget = (size_t)dev_smem;
 
     st->cpc = (NX <= 4096) ? 2 : 1;
     {
-        const char *e = getenv("PLATEFLEX_B200_RADIX");
-        st->maxlr = (e && atoi(e) == 16) ? 4 : 3;
         const char *c = getenv("PLATEFLEX_B200_CTAS");
         if (c && atoi(c) > 0) st->ctas_per_transform = atoi(c);
     }
@@ -613,8 +202,8 @@ int plan_init_pruned(pfx_plan *pl)
             kbmax = std::max(kbmax, sd.kb[ia]);
             sd.ce[ia] = c.norm * c.e0[ia];
         }
-        plan_axis(sd.ax, NX, std::max(kamax, 1), nx, budget, st->cpc, st->maxlr);
-        plan_axis(sd.ay, NY, std::max(kbmax, 1), ny, budget, 1, st->maxlr);
+        plan_axis(sd.ax, NX, std::max(kamax, 1), nx, budget, st->cpc);
+        plan_axis(sd.ay, NY, std::max(kbmax, 1), ny, budget, 1);
         sd.kamax = std::max(kamax, 1);
         sd.tabu = tabu_n;
         sd.tabv = tabv_n;
@@ -625,8 +214,8 @@ int plan_init_pruned(pfx_plan *pl)
         twa_n += (size_t)PFX_NA * NX;
         twb_n += (size_t)PFX_NA * NY;
         kamax_all = std::max(kamax_all, (size_t)sd.kamax);
-        st->smem1 = std::max(st->smem1, smem_bytes(sd.ay, 1));
-        st->smem2 = std::max(st->smem2, smem_bytes(sd.ax, st->cpc));
+        st->smem1 = std::max(st->smem1, prn_smem_bytes(sd.ay, 1));
+        st->smem2 = std::max(st->smem2, prn_smem_bytes(sd.ax, st->cpc));
     }
     if (st->smem1 > (size_t)dev_smem || st->smem2 > (size_t)dev_smem) {
         set_error("pruned engine: a %d x %d padded line does not fit in shared memory; use the dense engine", NX, NY);
@@ -705,12 +294,11 @@ int plan_init_pruned(pfx_plan *pl)
     }
     for (int g = 0; g < 2; g++) PFX_CUFFT(cufftSetWorkArea(st->fft_z[g], pl->d_fft_work));
 
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem1));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem1));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
-    PFX_CUDA(cudaFuncSetAttribute(pruned_pass2_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem2));
+    for (int is = 0; is < ns; is++) {
+        const ScaleDesc &sd = st->sd[is];
+        PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
+        PFX_CHECK(prn_configure_pass2(sd.ax.logL, sd.ax.pad, st->cpc, st->smem2));
+    }
     return PFX_OK;
 }
 
@@ -772,24 +360,12 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     a.T = st->T;
     a.W = st->W;
     const ScaleDesc &sd = a.sd;
-    const size_t sm1 = smem_bytes(sd.ay, 1), sm2 = smem_bytes(sd.ax, st->cpc);
+    const size_t sm1 = prn_smem_bytes(sd.ay, 1), sm2 = prn_smem_bytes(sd.ax, st->cpc);
     const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
     dim3 g1(std::min(sd.kamax, st->ctas_per_transform), PFX_NA * ngrids);
     dim3 g2(std::min(ngroups, st->ctas_per_transform), PFX_NA * ngrids);
-    if (st->maxlr >= 4) {
-        pruned_pass1_kernel<4><<<g1, NT, sm1, pl->stream>>>(a);
-        if (st->cpc == 2)
-            pruned_pass2_kernel<2, 4><<<g2, NT, sm2, pl->stream>>>(a);
-        else
-            pruned_pass2_kernel<1, 4><<<g2, NT, sm2, pl->stream>>>(a);
-    } else {
-        pruned_pass1_kernel<3><<<g1, NT, sm1, pl->stream>>>(a);
-        if (st->cpc == 2)
-            pruned_pass2_kernel<2, 3><<<g2, NT, sm2, pl->stream>>>(a);
-        else
-            pruned_pass2_kernel<1, 3><<<g2, NT, sm2, pl->stream>>>(a);
-    }
-    PFX_CUDA(cudaGetLastError());
+    PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
+    PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
     for (int ia = 0; ia < PFX_NA; ia++) st->cur_ce[ia] = sd.ce[ia];
     pl->launches += 2;
     return PFX_OK;

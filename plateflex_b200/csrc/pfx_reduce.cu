@@ -16,6 +16,20 @@ namespace {
 
 constexpr int NA = PFX_NA;
 
+// 1/x to ~1 ulp without the special-case branches of the IEEE division sequence: the hardware
+// seed (rcp.approx.ftz.f64, >= 20 bits) and two Newton steps.  x == 0 or non-finite yields inf / NaN,
+// which the callers replace by the reference's guarded values.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 __device__ __forceinline__ double jk_spread(const double (&v2)[NA])
 {
     // cpwt_sub.f90:144-152 / 344-357: mean of the NA delete-one values, then
@@ -23,11 +37,11 @@ __device__ __forceinline__ double jk_spread(const double (&v2)[NA])
     double m = 0.0;
 #pragma unroll
     for (int a = 0; a < NA; a++) m += v2[a];
-    m = m / (double)NA;
+    m = m * (1.0 / (double)NA);
     double d = 0.0;
 #pragma unroll
     for (int a = 0; a < NA; a++) d = d + (v2[a] - m) * (v2[a] - m);
-    d = sqrt(d * (double)(NA - 1) / (double)NA);
+    d = sqrt(d * ((double)(NA - 1) / (double)NA));
     return (d != d) ? 0.0 : d;
 }
 
@@ -47,7 +61,7 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
             q += s[a2];
             acc += q;
         }
-        v2[a] = acc / (double)(NA - 1);
+        v2[a] = acc * (1.0 / (double)(NA - 1));
         if (a < NA - 1) {
             p += s[a];
             cum += p;
@@ -59,18 +73,13 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
 __device__ __forceinline__ void ratio(double q1, double q2, double qx, double &ad, double &co)
 {
     // cpwt_sub.f90:329-335: co = Re(xp)^2/(p1*p2), ad = Re(xp)/p1, both 0 when a sum is 0.
-    // One reciprocal serves both quotients (ad = xp*p2/(p1*p2)); the results differ from two
-    // IEEE divisions by a few ulp, far inside the 1e-9 parity budget, at ~40% of the FP64 work.
-    const double den = q1 * q2;
-    if (q1 != 0.0 && q2 != 0.0) {
-        const double r = 1.0 / den;
-        const double xr = qx * r;
-        co = qx * xr;
-        ad = q2 * xr;
-    } else {
-        co = 0.0;
-        ad = 0.0;
-    }
+    // One branch-free reciprocal serves both quotients (ad = xp*p2/(p1*p2)), and the divisions by the
+    // constants na, na-1 are multiplications: the results differ from the reference's IEEE divisions by
+    // a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
+    const double xr = qx * fast_rcp(q1 * q2);
+    const bool ok = (q1 != 0.0) & (q2 != 0.0);
+    co = ok ? qx * xr : 0.0;
+    ad = ok ? q2 * xr : 0.0;
 }
 
 // cpwt_sub.f90:298-366, same shared-prefix walk: 10 + 55 ratio evaluations
@@ -93,8 +102,8 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             sa += ad;
             sc += co;
         }
-        ad2[a] = sa / (double)(NA - 1);
-        co2[a] = sc / (double)(NA - 1);
+        ad2[a] = sa * (1.0 / (double)(NA - 1));
+        co2[a] = sc * (1.0 / (double)(NA - 1));
         if (a < NA - 1) {
             p1 += s1[a];
             p2 += s2[a];
@@ -122,7 +131,7 @@ __device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
                   double *__restrict__ out2, double *__restrict__ out3)
 {
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(128)
             s[a] = fabs(w.x * w.x + w.y * w.y);  // CABS(w*CONJG(w)), cpwt.f90:224
             tot += s[a];
         }
-        out0[o] = tot / (double)NA;  // cpwt.f90:234
+        out0[o] = tot * (1.0 / (double)NA);  // cpwt.f90:234
         out1[o] = jk_sgram(s);
     } else if (MODE == RED_XSCALOGRAM) {
         double xr[NA], xi[NA];
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(128)
             tr += xr[a];
             ti += xi[a];
         }
-        reinterpret_cast<double2 *>(out0)[o] = make_double2(tr / (double)NA, ti / (double)NA);
+        reinterpret_cast<double2 *>(out0)[o] = make_double2(tr * (1.0 / (double)NA), ti * (1.0 / (double)NA));
         const double er = jk_sgram(xr), ei = jk_sgram(xi);
         out1[o] = sqrt(er * er + ei * ei);  // cpwt.f90:290
     } else {
@@ -171,9 +180,9 @@ __global__ void __launch_bounds__(128)
             t2 += s2[a];
             tx += xr[a];
         }
-        t1 = t1 / (double)NA;  // cpwt.f90:348-350
-        t2 = t2 / (double)NA;
-        tx = tx / (double)NA;
+        t1 = t1 * (1.0 / (double)NA);  // cpwt.f90:348-350
+        t2 = t2 * (1.0 / (double)NA);
+        tx = tx * (1.0 / (double)NA);
         out0[o] = tx / t1;                // cpwt.f90:354
         out2[o] = (tx * tx) / (t1 * t2);  // cpwt.f90:355
         double ead, eco;
