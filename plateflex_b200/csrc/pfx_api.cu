@@ -158,6 +158,19 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
     for (int g = 0; g < 2; g++)
         if ((rc = pl->alloc((void **)&pl->d_spec[g], P * sizeof(double2)))) return fail(rc);
     if ((rc = plan_init_axes(pl))) return fail(rc);
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&pl->s_aux, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->s_copy, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+            e = cudaEventCreateWithFlags(&pl->ev_planes[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_reduced[b], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            set_error("stream / event creation failed: %s", cudaGetErrorString(e));
+            return fail(PFX_ERR_CUDA);
+        }
+    }
 
     // forward FFT plan (cpwt.f90:122): one 2-D Z2Z per grid, work area owned by the plan
     {
@@ -194,6 +207,13 @@ int pfx_plan_destroy(pfx_plan *pl)
     DeviceGuard guard(pl->device);
     cudaDeviceSynchronize();
     plan_free_pruned(pl);
+    if (pl->s_aux) cudaStreamDestroy(pl->s_aux);
+    if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    for (int b = 0; b < 2; b++) {
+        if (pl->ev_planes[b]) cudaEventDestroy(pl->ev_planes[b]);
+        if (pl->ev_reduced[b]) cudaEventDestroy(pl->ev_reduced[b]);
+    }
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     if (pl->fft_fwd_ok) cufftDestroy(pl->fft_fwd);
     for (int g = 0; g < 2; g++)
         if (pl->fft_inv_ok[g]) cufftDestroy(pl->fft_inv[g]);
@@ -256,41 +276,71 @@ int check_range(const pfx_plan *pl, int is0, int is1)
     return PFX_OK;
 }
 
-int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *o0, double *o1,
-            double *o2, double *o3)
+// h_outs (optional): host destinations of the outputs; each finished scale is copied back on the copy
+// stream while later scales are still being computed.  elems[i] = doubles per cell of output i.
+int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *d_outs,
+            double *const *h_outs, const int *elems, int nouts)
 {
     const int ngrids = g2 ? 2 : 1;
     const size_t nxy = (size_t)pl->nx * pl->ny;
     PFX_CHECK(forward_spectrum(pl, g1, 0));
     if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
-    if (pl->engine == PFX_ENGINE_PRUNED) PFX_CHECK(pruned_prepare(pl, ngrids));
+    const bool pruned = pl->engine == PFX_ENGINE_PRUNED;
+    if (pruned) PFX_CHECK(pruned_prepare(pl, ngrids));
+    // With two plane buffers (pruned engine) the reduction of scale s overlaps the passes of scale s+1.
+    const int nbuf = pruned ? pruned_num_buffers(pl) : 1;
+    const bool overlap = nbuf == 2 && mode != OUT_CUBE;
+    cudaStream_t red_stream = overlap ? pl->s_aux : pl->stream;
     for (int is = is0; is < is1; is++) {
+        const int b = (is - is0) & 1;
         const size_t so = (size_t)(is - is0) * nxy;
         PlaneView v1, v2;
-        if (pl->engine == PFX_ENGINE_DENSE) {
+        if (!pruned) {
             PFX_CHECK(dense_scale_planes(pl, is, ngrids));
             v1 = dense_view(pl, 0);
             v2 = dense_view(pl, ngrids - 1);
         } else {
+            if (overlap) {
+                pruned_select_buffer(pl, b);
+                if (is - is0 >= 2) PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_reduced[b], 0));
+            }
             PFX_CHECK(pruned_scale_planes(pl, is, ngrids));
             v1 = pruned_view(pl, 0);
             v2 = pruned_view(pl, ngrids - 1);
         }
+        if (overlap) {
+            PFX_CUDA(cudaEventRecord(pl->ev_planes[b], pl->stream));
+            PFX_CUDA(cudaStreamWaitEvent(red_stream, pl->ev_planes[b], 0));
+        }
         if (mode == OUT_CUBE) {
-            PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(o0) + so * PFX_NA, pl->stream));
-        } else if (mode == RED_XSCALOGRAM) {
-            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o0 + 2 * so, o1 + so, nullptr, nullptr, pl->stream));
+            PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, red_stream));
         } else {
-            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o0 + so, o1 + so, o2 ? o2 + so : nullptr,
-                                    o3 ? o3 + so : nullptr, pl->stream));
+            double *o[4] = {nullptr, nullptr, nullptr, nullptr};
+            for (int i = 0; i < nouts; i++) o[i] = d_outs[i] + so * elems[i];
+            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream));
         }
         pl->launches++;
+        if (overlap || h_outs) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));
+        if (h_outs) {
+            PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_reduced[b], 0));
+            for (int i = 0; i < nouts; i++)
+                PFX_CUDA(cudaMemcpyAsync(h_outs[i] + so * elems[i], d_outs[i] + so * elems[i],
+                                         nxy * elems[i] * sizeof(double), cudaMemcpyDeviceToHost, pl->s_copy));
+        }
+    }
+    // join the internal streams back into the caller's stream
+    if (overlap) {
+        PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_aux));
+        PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
+    }
+    if (h_outs) {
+        PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_copy));
+        PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
     }
     return PFX_OK;
 }
 
-// Host wrapper: stage the inputs, run, copy the outputs back, synchronise.
-// outs[i] has out_elems[i] doubles per scale.
+// Host wrapper: stage the inputs, run, stream the outputs back scale by scale, synchronise.
 int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *outs,
                  const int *out_elems_per_cell, int nouts)
 {
@@ -307,10 +357,7 @@ int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int
     double *d_o[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < nouts; i++)
         PFX_CHECK(pl->scratch(2 + i, nxy * nsc * out_elems_per_cell[i] * sizeof(double), (void **)&d_o[i]));
-    PFX_CHECK(run_cwt(pl, mode, d_g[0], d_g[1], is0, is1, d_o[0], d_o[1], d_o[2], d_o[3]));
-    for (int i = 0; i < nouts; i++)
-        PFX_CUDA(cudaMemcpyAsync(outs[i], d_o[i], nxy * nsc * out_elems_per_cell[i] * sizeof(double),
-                                 cudaMemcpyDeviceToHost, pl->stream));
+    PFX_CHECK(run_cwt(pl, mode, d_g[0], d_g[1], is0, is1, d_o, outs, out_elems_per_cell, nouts));
     PFX_CUDA(cudaStreamSynchronize(pl->stream));
     return PFX_OK;
 }
@@ -324,7 +371,9 @@ int pfx_wlet_transform_dev(pfx_plan *pl, const double *grid, int is0, int is1, d
     PFX_CHECK(check_range(pl, is0, is1));
     PFX_ARG(grid && cube, "null pointer");
     DeviceGuard guard(pl->device);
-    return run_cwt(pl, OUT_CUBE, grid, nullptr, is0, is1, cube, nullptr, nullptr, nullptr);
+    double *outs[1] = {cube};
+    const int el[1] = {2 * PFX_NA};
+    return run_cwt(pl, OUT_CUBE, grid, nullptr, is0, is1, outs, nullptr, el, 1);
 }
 
 int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, double *cube)
@@ -363,7 +412,9 @@ int pfx_wlet_scalogram_dev(pfx_plan *pl, const double *grid, int is0, int is1, d
     PFX_CHECK(check_range(pl, is0, is1));
     PFX_ARG(grid && wl_sg && ewl_sg, "null pointer");
     DeviceGuard guard(pl->device);
-    return run_cwt(pl, RED_SCALOGRAM, grid, nullptr, is0, is1, wl_sg, ewl_sg, nullptr, nullptr);
+    double *outs[2] = {wl_sg, ewl_sg};
+    const int el[2] = {1, 1};
+    return run_cwt(pl, RED_SCALOGRAM, grid, nullptr, is0, is1, outs, nullptr, el, 2);
 }
 
 int pfx_wlet_scalogram_host(pfx_plan *pl, const double *grid, int is0, int is1, double *wl_sg, double *ewl_sg)
@@ -381,7 +432,9 @@ int pfx_wlet_xscalogram_dev(pfx_plan *pl, const double *g1, const double *g2, in
     PFX_CHECK(check_range(pl, is0, is1));
     PFX_ARG(g1 && g2 && wl_xsg && ewl_xsg, "null pointer");
     DeviceGuard guard(pl->device);
-    return run_cwt(pl, RED_XSCALOGRAM, g1, g2, is0, is1, wl_xsg, ewl_xsg, nullptr, nullptr);
+    double *outs[2] = {wl_xsg, ewl_xsg};
+    const int el[2] = {2, 1};
+    return run_cwt(pl, RED_XSCALOGRAM, g1, g2, is0, is1, outs, nullptr, el, 2);
 }
 
 int pfx_wlet_xscalogram_host(pfx_plan *pl, const double *g1, const double *g2, int is0, int is1, double *wl_xsg,
@@ -400,7 +453,9 @@ int pfx_wlet_admit_coh_dev(pfx_plan *pl, const double *topo, const double *grav,
     PFX_CHECK(check_range(pl, is0, is1));
     PFX_ARG(topo && grav && wl_admit && ewl_admit && wl_coh && ewl_coh, "null pointer");
     DeviceGuard guard(pl->device);
-    return run_cwt(pl, RED_ADMIT_COH, topo, grav, is0, is1, wl_admit, ewl_admit, wl_coh, ewl_coh);
+    double *outs[4] = {wl_admit, ewl_admit, wl_coh, ewl_coh};
+    const int el[4] = {1, 1, 1, 1};
+    return run_cwt(pl, RED_ADMIT_COH, topo, grav, is0, is1, outs, nullptr, el, 4);
 }
 
 int pfx_wlet_admit_coh_host(pfx_plan *pl, const double *topo, const double *grav, int is0, int is1, double *wl_admit,

@@ -135,7 +135,7 @@ struct PrunedState {
     double2 *rootx = nullptr, *rooty = nullptr;
     double *tabu = nullptr, *tabv = nullptr;
     double2 *twa = nullptr, *twb = nullptr;
-    double2 *T = nullptr, *W = nullptr, *zc = nullptr, *zplanes = nullptr;
+    double2 *T = nullptr, *W = nullptr, *Wbuf[2] = {nullptr, nullptr}, *zc = nullptr, *zplanes = nullptr;
     cufftHandle fft_z[2] = {0, 0};
     bool fft_z_ok[2] = {false, false};
     size_t smem1 = 0, smem2 = 0;
@@ -229,7 +229,8 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CHECK(dalloc((void **)&st->twa, twa_n * sizeof(double2)));
     PFX_CHECK(dalloc((void **)&st->twb, twb_n * sizeof(double2)));
     PFX_CHECK(dalloc((void **)&st->T, 2 * PFX_NA * kamax_all * ny * sizeof(double2)));
-    PFX_CHECK(dalloc((void **)&st->W, 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
+    for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Wbuf[b], 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
+    st->W = st->Wbuf[0];
     PFX_CHECK(dalloc((void **)&st->zc, 2 * (size_t)nx * ny * sizeof(double2)));
     PFX_CHECK(dalloc((void **)&st->zplanes, 2 * P * sizeof(double2)));
 
@@ -370,6 +371,10 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     pl->launches += 2;
     return PFX_OK;
 }
+
+int pruned_num_buffers(const pfx_plan *pl) { return pl->pruned ? 2 : 1; }
+
+void pruned_select_buffer(pfx_plan *pl, int b) { state_of(pl)->W = state_of(pl)->Wbuf[b & 1]; }
 
 PlaneView pruned_view(const pfx_plan *pl, int g)
 {

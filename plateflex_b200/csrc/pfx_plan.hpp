@@ -42,6 +42,12 @@ struct pfx_plan {
 
     void *pruned = nullptr;  // PrunedState of pfx_cwt_pruned.cu
 
+    // Internal streams: the azimuth reduction of scale s runs on s_aux while the transform passes of
+    // scale s+1 run on the caller's stream (two plane buffers); the host entry points drain finished
+    // scales to the host on s_copy.  Everything is joined back into `stream` before a call returns.
+    cudaStream_t s_aux = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_planes[2] = {nullptr, nullptr}, ev_reduced[2] = {nullptr, nullptr}, ev_join = nullptr;
+
     // grow-only scratch used by the _host entry points (inputs / outputs staging)
     void *d_scratch[8] = {};
     size_t scratch_bytes[8] = {};
@@ -72,5 +78,7 @@ void plan_free_pruned(pfx_plan *pl);
 int pruned_prepare(pfx_plan *pl, int ngrids);          // admissibility transform Z, once per set of spectra
 int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);  // -> compact W planes of scale `is`
 PlaneView pruned_view(const pfx_plan *pl, int g);
+int pruned_num_buffers(const pfx_plan *pl);
+void pruned_select_buffer(pfx_plan *pl, int b);
 
 }  // namespace pfx
