@@ -19,6 +19,8 @@
 // One group of G lanes per grid cell, scales strided over the lanes; all lanes
 // of a group carry identical copies of the small dense algebra.
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 
 #include "pfx_flex.cuh"
 
@@ -391,6 +393,300 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask)
     return v;
 }
 
+// ---- trf_bounds (scipy/optimize/_lsq/trf.py), n = NP <= 3 -----------------------------------
+// evaluate(x, normal) fills cost = 0.5*sum r^2, g = J^T r and B = J^T J at x.  Returns SciPy's
+// termination status (1 gtol, 2 ftol, 3 xtol, 4 both), -1 when max_nfev was reached, -3 when the
+// residuals are not finite at the starting point; x / cur hold the final point.
+template <int NP, class Eval>
+__device__ __forceinline__ int trf_minimize(const Eval &evaluate, int m, double (&x)[NP], Normal<NP> &cur)
+{
+    // estimate.py:271,280,290,299
+    const double lb[3] = {2., 0.0001, 0.0001};
+    const double ub[3] = {250., 0.9999, FLEX_PI - 0.001};
+    double lbp[NP], ubp[NP];
+    const double x0[3] = {20., 0.5, FLEX_PI / 2.};  // estimate.py:271,290
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        x[p] = x0[p];
+        lbp[p] = lb[p];
+        ubp[p] = ub[p];
+    }
+    Normal<NP> trial;
+    evaluate(x, cur);
+    int nfev = 1, status = -1;
+    double v[NP], dv[NP];
+    cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+    double Delta;
+    {
+        double t[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) t[p] = x[p] / sqrt(v[p]);
+        Delta = vnorm<NP>(t);
+        if (Delta == 0.) Delta = 1.;
+    }
+    double alpha = 0.;
+    if (!isfinite(cur.cost)) status = -3;  // "Residuals are not finite in the initial point"
+    while (status == -1) {
+        cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+        double g_norm = 0.;
+#pragma unroll
+        for (int p = 0; p < NP; p++) g_norm = fmax(g_norm, fabs(cur.g[p] * v[p]));
+        if (g_norm < TRF_GTOL) status = 1;
+        if (status != -1 || nfev >= TRF_MAX_NFEV) break;
+        double d[NP], diag_h[NP], g_h[NP], Bh[NP][NP], Bw[NP][NP], lam[NP], V[NP][NP], suf[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            d[p] = sqrt(v[p]);
+            diag_h[p] = cur.g[p] * dv[p];
+            g_h[p] = d[p] * cur.g[p];
+        }
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int q = 0; q < NP; q++) {
+                Bh[p][q] = d[p] * d[q] * cur.B[p][q] + ((p == q) ? diag_h[p] : 0.);
+                Bw[p][q] = Bh[p][q];
+            }
+        jacobi_eig<NP>(Bw, lam, V);
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            double sacc = 0.;
+#pragma unroll
+            for (int q = 0; q < NP; q++) sacc += V[q][p] * g_h[q];
+            suf[p] = sacc;
+        }
+        const double theta = fmax(0.995, 1. - g_norm);
+        double actual = -1., step_norm = 0.;
+        double xn[NP];
+        while (actual <= 0. && nfev < TRF_MAX_NFEV) {
+            double p_h[NP], pp[NP], step[NP], step_h[NP], predicted;
+            solve_tr<NP>(m, lam, V, suf, Delta, alpha, p_h);
+#pragma unroll
+            for (int p = 0; p < NP; p++) pp[p] = d[p] * p_h[p];
+            select_step<NP>(x, Bh, g_h, pp, p_h, d, Delta, lbp, ubp, theta, step, step_h, predicted);
+#pragma unroll
+            for (int p = 0; p < NP; p++) {  // make_strictly_feasible(x + step, rstep=0)
+                double t = x[p] + step[p];
+                if (t <= lbp[p]) t = nextafter(lbp[p], ubp[p]);
+                else if (t >= ubp[p]) t = nextafter(ubp[p], lbp[p]);
+                xn[p] = t;
+            }
+            evaluate(xn, trial);
+            nfev++;
+            const double step_h_norm = vnorm<NP>(step_h);
+            if (!isfinite(trial.cost)) {
+                Delta = 0.25 * step_h_norm;
+                continue;
+            }
+            actual = cur.cost - trial.cost;
+            // update_tr_radius
+            double ratio, Delta_new = Delta;
+            if (predicted > 0.) ratio = actual / predicted;
+            else if (predicted == 0. && actual == 0.) ratio = 1.;
+            else ratio = 0.;
+            if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
+            else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
+            step_norm = vnorm<NP>(step);
+            // check_termination
+            const bool f_ok = (actual < TRF_FTOL * cur.cost) && (ratio > 0.25);
+            const bool x_ok = step_norm < TRF_XTOL * (TRF_XTOL + vnorm<NP>(x));
+            if (f_ok && x_ok) status = 4;
+            else if (f_ok) status = 2;
+            else if (x_ok) status = 3;
+            if (status != -1) break;
+            alpha *= Delta / Delta_new;
+            Delta = Delta_new;
+        }
+        if (actual > 0.) {
+#pragma unroll
+            for (int p = 0; p < NP; p++) x[p] = xn[p];
+            cur = trial;
+        }
+    }
+    return status;
+}
+
+// Covariance (curve_fit, _minpack_py.py:1050-1054: pseudo-inverse of J^T J through its singular values,
+// absolute_sigma=True), reduced chi-square (estimate.py:286-287) and the output maps of one cell.
+template <int NP>
+__device__ __forceinline__ void write_cell(const FitArgs &a, size_t dst, int m, const double (&x)[NP],
+                                           const Normal<NP> &cur, int status)
+{
+    double Bc[NP][NP], lam[NP], V[NP][NP], sd[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int q = 0; q < NP; q++) Bc[p][q] = cur.B[p][q];
+    jacobi_eig<NP>(Bc, lam, V);
+    const double s0 = sqrt(fmax(lam[0], 0.));
+    const double thr = DBL_EPS * (double)((m > NP) ? m : NP) * s0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        double c = 0.;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const double sq = sqrt(fmax(lam[q], 0.));
+            if (sq > thr) c += V[p][q] * V[p][q] / lam[q];
+        }
+        sd[p] = sqrt(c);
+    }
+    a.o_te[dst] = x[0];
+    a.o_te_std[dst] = sd[0];
+    a.o_f[dst] = x[1];
+    a.o_f_std[dst] = sd[1];
+    if (NP == 3) {
+        a.o_a[dst] = x[NP - 1];
+        a.o_a_std[dst] = sd[NP - 1];
+    }
+    a.o_chi2[dst] = 2. * cur.cost / (double)(m - NP);
+    if (a.status) a.status[dst] = (status > 0) ? 1 : ((status == -3) ? 3 : 2);
+}
+
+__device__ __forceinline__ void write_bad_cell(const FitArgs &a, size_t dst, bool with_alpha)
+{
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    a.o_te[dst] = a.o_te_std[dst] = a.o_f[dst] = a.o_f_std[dst] = a.o_chi2[dst] = nanv;
+    if (with_alpha) a.o_a[dst] = a.o_a_std[dst] = nanv;
+    if (a.status) a.status[dst] = 3;
+}
+
+// accumulate one residual row (r, jr[NP]) into acc = [sum r^2, J^T r (NP), upper triangle of J^T J]
+template <int NP>
+__device__ __forceinline__ void accumulate(double (&acc)[1 + NP + NP * (NP + 1) / 2], double r, const double (&jr)[NP])
+{
+    acc[0] += r * r;
+    int q = 1 + NP;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        acc[1 + p] += jr[p] * r;
+#pragma unroll
+        for (int p2 = p; p2 < NP; p2++) acc[q++] += jr[p] * jr[p2];
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void unpack(const double (&acc)[1 + NP + NP * (NP + 1) / 2], Normal<NP> &nm)
+{
+    nm.cost = 0.5 * acc[0];
+    int q = 1 + NP;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        nm.g[p] = acc[1 + p];
+#pragma unroll
+        for (int p2 = p; p2 < NP; p2++) {
+            nm.B[p][p2] = acc[q];
+            nm.B[p2][p] = acc[q];
+            q++;
+        }
+    }
+}
+
+__device__ __forceinline__ double rcp_nr(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// ---- thread-per-cell fit kernel ----------------------------------------------------------------
+// One thread per grid cell, consecutive threads on consecutive x so that every load of the
+// (nx, ny, ns) maps is a coalesced 256-byte warp access; the scale axis is walked serially and
+// the maps are re-read (from L1/L2) at every model evaluation, only the depth attenuation factors
+// exp(-k*(zc+wd)), exp(-k*wd) are kept per thread in shared memory.  No lane ever idles on the
+// small dense algebra of the optimiser, which made this 3x cheaper than one warp per cell.
+constexpr int FIT_NT = 128;
+
+template <int NP>
+__global__ void __launch_bounds__(FIT_NT) fit_cell_kernel(FitArgs a)
+{
+    extern __shared__ double fsh[];
+    double *k4 = fsh;                              // [ns] k^4 * Em*1e9/12/(1-nu^2)
+    double *sdeep = fsh + a.ns;                    // [ns][FIT_NT]
+    double *stop = sdeep + (size_t)a.ns * FIT_NT;  // [ns][FIT_NT] (free-air only)
+    for (int s = threadIdx.x; s < a.ns; s += FIT_NT) {
+        const double k2 = a.k[s] * a.k[s];
+        k4[s] = (k2 * k2) * (FLEX_EM * 1.e9 / 12. / (1. - FLEX_NU * FLEX_NU));
+    }
+    __syncthreads();
+    const long long ncells = (long long)a.fx * a.fy;
+    const size_t nxy = (size_t)a.nx * a.ny;
+    const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
+    const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
+    const bool freeair = a.conf.boug != 1;
+    const int tid = threadIdx.x;
+    for (long long cell = (long long)blockIdx.x * FIT_NT + tid; cell < ncells; cell += (long long)gridDim.x * FIT_NT) {
+        const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
+        const size_t src = (size_t)(cj * a.nn) * a.nx + (size_t)ci * a.nn;
+        const size_t dst = (size_t)cj * a.mx + ci;
+        if (a.mask && a.mask[src]) continue;  // classes.py:1228-1231 (outputs stay zero)
+        const double rhoc = a.rhoc_map ? a.rhoc_map[src] : a.conf.rhoc;  // classes.py:1087-1091
+        const double zc = a.zc_map ? a.zc_map[src] : a.conf.zc;
+        const FlexCell fc = flex_cell(a.conf, rhoc, zc, a.wd[src]);
+        bool bad = false;
+        for (int s = 0; s < a.ns; s++) {
+            const FlexK q = flex_k(fc, a.k[s]);
+            sdeep[s * FIT_NT + tid] = q.deep;
+            if (freeair) stop[s * FIT_NT + tid] = q.top;
+            const size_t o = src + nxy * s;
+            if (use_adm) {
+                const double y = __ldg(a.adm + o), e = __ldg(a.eadm + o);
+                bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+            }
+            if (use_coh) {
+                const double y = __ldg(a.coh + o), e = __ldg(a.ecoh + o);
+                bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+            }
+        }
+        if (bad) {  // SciPy raises ValueError here; we flag the cell
+            write_bad_cell(a, dst, NP == 3);
+            continue;
+        }
+        auto evaluate = [&](const double(&x)[NP], Normal<NP> &nm) {
+            const double te = x[0], F = x[1];
+            const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
+            double sa, ca;
+            sincos(alpha, &sa, &ca);
+            const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+            double acc[1 + NP + NP * (NP + 1) / 2];
+#pragma unroll
+            for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
+            for (int s = 0; s < a.ns; s++) {
+                FlexK fk;
+                fk.k4d = k4[s];
+                fk.deep = sdeep[s * FIT_NT + tid];
+                fk.top = freeair ? stop[s * FIT_NT + tid] : 0.;
+                double adm, coh, dA[3], dC[3];
+                flex_eval<true>(fc, fk, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+                const size_t o = src + nxy * s;
+                if (use_adm) {
+                    const double w = rcp_nr(__ldg(a.eadm + o));  // curve_fit: transform = 1/sigma
+                    const double r = (adm - __ldg(a.adm + o)) * w;
+                    double jr[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) jr[p] = dA[p] * w;
+                    accumulate<NP>(acc, r, jr);
+                }
+                if (use_coh) {
+                    const double w = rcp_nr(__ldg(a.ecoh + o));
+                    const double r = (coh - __ldg(a.coh + o)) * w;
+                    double jr[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) jr[p] = dC[p] * w;
+                    accumulate<NP>(acc, r, jr);
+                }
+            }
+            unpack<NP>(acc, nm);
+        };
+        double x[NP];
+        Normal<NP> cur;
+        const int status = trf_minimize<NP>(evaluate, m, x, cur);
+        write_cell<NP>(a, dst, m, x, cur, status);
+    }
+}
+
 // ---- the fit kernel ---------------------------------------------------------------
 // G lanes per cell, NSL scales per lane (ns <= G*NSL), NP fitted parameters.
 template <int G, int NSL, int NP>
@@ -404,10 +700,6 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
     const size_t nxy = (size_t)a.nx * a.ny;
     const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
     const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
-
-    // estimate.py:271,280,290,299
-    const double lb[3] = {2., 0.0001, 0.0001};
-    const double ub[3] = {250., 0.9999, FLEX_PI - 0.001};
 
     for (long long cell = group; cell < ncells; cell += ngroups) {
         const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
@@ -518,140 +810,11 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
             }
         };
 
-        // ---- trf_bounds (scipy/optimize/_lsq/trf.py) ----
-        double x[NP], lbp[NP], ubp[NP];
-        const double x0[3] = {20., 0.5, FLEX_PI / 2.};  // estimate.py:271,290
-#pragma unroll
-        for (int p = 0; p < NP; p++) {
-            x[p] = x0[p];
-            lbp[p] = lb[p];
-            ubp[p] = ub[p];
-        }
-        Normal<NP> cur, trial;
-        evaluate(x, cur);
-        int nfev = 1, status = -1;
-        double v[NP], dv[NP];
-        cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
-        double Delta;
-        {
-            double t[NP];
-#pragma unroll
-            for (int p = 0; p < NP; p++) t[p] = x[p] / sqrt(v[p]);
-            Delta = vnorm<NP>(t);
-            if (Delta == 0.) Delta = 1.;
-        }
-        double alpha = 0.;
-        if (!isfinite(cur.cost)) status = -3;  // "Residuals are not finite in the initial point"
-        while (status == -1) {
-            cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
-            double g_norm = 0.;
-#pragma unroll
-            for (int p = 0; p < NP; p++) g_norm = fmax(g_norm, fabs(cur.g[p] * v[p]));
-            if (g_norm < TRF_GTOL) status = 1;
-            if (status != -1 || nfev >= TRF_MAX_NFEV) break;
-            double d[NP], diag_h[NP], g_h[NP], Bh[NP][NP], Bw[NP][NP], lam[NP], V[NP][NP], suf[NP];
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-                d[p] = sqrt(v[p]);
-                diag_h[p] = cur.g[p] * dv[p];
-                g_h[p] = d[p] * cur.g[p];
-            }
-#pragma unroll
-            for (int p = 0; p < NP; p++)
-#pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    Bh[p][q] = d[p] * d[q] * cur.B[p][q] + ((p == q) ? diag_h[p] : 0.);
-                    Bw[p][q] = Bh[p][q];
-                }
-            jacobi_eig<NP>(Bw, lam, V);
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-                double s = 0.;
-#pragma unroll
-                for (int q = 0; q < NP; q++) s += V[q][p] * g_h[q];
-                suf[p] = s;
-            }
-            const double theta = fmax(0.995, 1. - g_norm);
-            double actual = -1., step_norm = 0.;
-            double xn[NP];
-            while (actual <= 0. && nfev < TRF_MAX_NFEV) {
-                double p_h[NP], pp[NP], step[NP], step_h[NP], predicted;
-                solve_tr<NP>(m, lam, V, suf, Delta, alpha, p_h);
-#pragma unroll
-                for (int p = 0; p < NP; p++) pp[p] = d[p] * p_h[p];
-                select_step<NP>(x, Bh, g_h, pp, p_h, d, Delta, lbp, ubp, theta, step, step_h, predicted);
-#pragma unroll
-                for (int p = 0; p < NP; p++) {  // make_strictly_feasible(x + step, rstep=0)
-                    double t = x[p] + step[p];
-                    if (t <= lbp[p]) t = nextafter(lbp[p], ubp[p]);
-                    else if (t >= ubp[p]) t = nextafter(ubp[p], lbp[p]);
-                    xn[p] = t;
-                }
-                evaluate(xn, trial);
-                nfev++;
-                const double step_h_norm = vnorm<NP>(step_h);
-                if (!isfinite(trial.cost)) {
-                    Delta = 0.25 * step_h_norm;
-                    continue;
-                }
-                actual = cur.cost - trial.cost;
-                // update_tr_radius
-                double ratio, Delta_new = Delta;
-                if (predicted > 0.) ratio = actual / predicted;
-                else if (predicted == 0. && actual == 0.) ratio = 1.;
-                else ratio = 0.;
-                if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
-                else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
-                step_norm = vnorm<NP>(step);
-                // check_termination
-                const bool f_ok = (actual < TRF_FTOL * cur.cost) && (ratio > 0.25);
-                const bool x_ok = step_norm < TRF_XTOL * (TRF_XTOL + vnorm<NP>(x));
-                if (f_ok && x_ok) status = 4;
-                else if (f_ok) status = 2;
-                else if (x_ok) status = 3;
-                if (status != -1) break;
-                alpha *= Delta / Delta_new;
-                Delta = Delta_new;
-            }
-            if (actual > 0.) {
-#pragma unroll
-                for (int p = 0; p < NP; p++) x[p] = xn[p];
-                cur = trial;
-            }
-        }
+        double x[NP];
+        Normal<NP> cur;
+        const int status = trf_minimize<NP>(evaluate, m, x, cur);
 
-        // ---- covariance and outputs (curve_fit: _minpack_py.py:1050-1054, estimate.py:286-287,390) ----
-        if (lane == 0) {
-            double Bc[NP][NP], lam[NP], V[NP][NP], sd[NP];
-#pragma unroll
-            for (int p = 0; p < NP; p++)
-#pragma unroll
-                for (int q = 0; q < NP; q++) Bc[p][q] = cur.B[p][q];
-            jacobi_eig<NP>(Bc, lam, V);
-            const double s0 = sqrt(fmax(lam[0], 0.));
-            const double thr = DBL_EPS * (double)((m > NP) ? m : NP) * s0;
-#pragma unroll
-            for (int p = 0; p < NP; p++) {
-                double c = 0.;
-#pragma unroll
-                for (int q = 0; q < NP; q++) {
-                    const double sq = sqrt(fmax(lam[q], 0.));
-                    if (sq > thr) c += V[p][q] * V[p][q] / lam[q];
-                }
-                sd[p] = sqrt(c);
-            }
-            const double chi2 = 2. * cur.cost / (double)(m - NP);
-            a.o_te[dst] = x[0];
-            a.o_te_std[dst] = sd[0];
-            a.o_f[dst] = x[1];
-            a.o_f_std[dst] = sd[1];
-            if (NP == 3) {
-                a.o_a[dst] = x[NP - 1];
-                a.o_a_std[dst] = sd[NP - 1];
-            }
-            a.o_chi2[dst] = chi2;
-            if (a.status) a.status[dst] = (status > 0) ? 1 : ((status == -3) ? 3 : 2);
-        }
+        if (lane == 0) write_cell<NP>(a, dst, m, x, cur, status);
     }
 }
 
@@ -693,6 +856,25 @@ int launch_fit_np(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
         fit_kernel<G, NSL, 3><<<(unsigned)blocks, threads, 0, stream>>>(a);
     else
         fit_kernel<G, NSL, 2><<<(unsigned)blocks, threads, 0, stream>>>(a);
+    PFX_CUDA(cudaGetLastError());
+    return PFX_OK;
+}
+
+int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
+{
+    const long long ncells = (long long)a.fx * a.fy;
+    const size_t smem = ((size_t)a.ns + 2 * (size_t)a.ns * FIT_NT) * sizeof(double);
+    long long blocks = (ncells + FIT_NT - 1) / FIT_NT;
+    const long long cap = (long long)nsm * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (alph) {
+        PFX_CUDA(cudaFuncSetAttribute(fit_cell_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_cell_kernel<3><<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
+    } else {
+        PFX_CUDA(cudaFuncSetAttribute(fit_cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fit_cell_kernel<2><<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
+    }
     PFX_CUDA(cudaGetLastError());
     return PFX_OK;
 }
@@ -775,18 +957,23 @@ int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const do
         // range(0, nx-nn, nn) never reaches index mx*nn or beyond (classes.py:1218 vs 1189)
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-        if (ns <= 8)
-            rc = launch_fit_np<8, 1>(a, alph, st, nsm);
-        else if (ns <= 16)
-            rc = launch_fit_np<8, 2>(a, alph, st, nsm);
-        else if (ns <= 24)
-            rc = launch_fit_np<8, 3>(a, alph, st, nsm);
-        else if (ns <= 32)
-            rc = launch_fit_np<8, 4>(a, alph, st, nsm);
-        else if (ns <= 48)
-            rc = launch_fit_np<16, 3>(a, alph, st, nsm);
-        else
-            rc = launch_fit_np<16, 4>(a, alph, st, nsm);
+        const char *mode = getenv("PLATEFLEX_B200_FIT");
+        if (mode && !strcmp(mode, "group")) {  // cooperative variant: 8 or 16 lanes per cell
+            if (ns <= 8)
+                rc = launch_fit_np<8, 1>(a, alph, st, nsm);
+            else if (ns <= 16)
+                rc = launch_fit_np<8, 2>(a, alph, st, nsm);
+            else if (ns <= 24)
+                rc = launch_fit_np<8, 3>(a, alph, st, nsm);
+            else if (ns <= 32)
+                rc = launch_fit_np<8, 4>(a, alph, st, nsm);
+            else if (ns <= 48)
+                rc = launch_fit_np<16, 3>(a, alph, st, nsm);
+            else
+                rc = launch_fit_np<16, 4>(a, alph, st, nsm);
+        } else {
+            rc = launch_fit_cell(a, alph, st, nsm);
+        }
     }
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return rc;
