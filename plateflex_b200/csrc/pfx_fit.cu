@@ -598,9 +598,12 @@ __device__ __forceinline__ double rcp_nr(double x)
 // exp(-k*(zc+wd)), exp(-k*wd) are kept per thread in shared memory.  No lane ever idles on the
 // small dense algebra of the optimiser, which made this 3x cheaper than one warp per cell.
 constexpr int FIT_NT = 128;
+#ifndef FIT_MIN_BLOCKS
+#define FIT_MIN_BLOCKS 3
+#endif
 
 template <int NP>
-__global__ void __launch_bounds__(FIT_NT) fit_cell_kernel(FitArgs a)
+__global__ void __launch_bounds__(FIT_NT, FIT_MIN_BLOCKS) fit_cell_kernel(FitArgs a)
 {
     extern __shared__ double fsh[];
     double *k4 = fsh;                              // [ns] k^4 * Em*1e9/12/(1-nu^2)
@@ -653,6 +656,7 @@ __global__ void __launch_bounds__(FIT_NT) fit_cell_kernel(FitArgs a)
             double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
             for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
+#pragma unroll 2
             for (int s = 0; s < a.ns; s++) {
                 FlexK fk;
                 fk.k4d = k4[s];
