@@ -99,6 +99,15 @@ int pfx_plan_set_stream(pfx_plan *plan, void *stream);
 int pfx_plan_info(const pfx_plan *plan, int *nnx, int *nny, size_t *device_bytes);
 /* number of kernels / library launches this plan has enqueued so far (for bench.py's gpu_launches). */
 int pfx_plan_launch_count(const pfx_plan *plan, long long *kernels);
+/* Per-kernel device timers.  When enabled, every launch of the plan's kernels is bracketed by a CUDA
+ * event pair on the stream it is launched on; pfx_plan_profile_read waits for the recorded spans,
+ * returns the summed milliseconds and launch counts per kernel class and clears them.
+ * Classes (index): 0 forward spectrum, 1 admissibility transform, 2 pruned pass 1 (y transforms),
+ * 3 pruned pass 2 (x transforms), 4 azimuth reduction + jackknife, 5 dense daughter multiply,
+ * 6 dense inverse cuFFT, 7 wl_trans crop. */
+#define PFX_KERNEL_CLASSES 8
+int pfx_plan_profile_enable(pfx_plan *plan, int on);
+int pfx_plan_profile_read(pfx_plan *plan, double *ms, long long *count, int n);
 /* pruned engine: support half-width of the daughter in units of its k-space sigma (default 9.5). */
 int pfx_plan_set_cutoff(pfx_plan *plan, double nsigma);
 
@@ -168,6 +177,21 @@ int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const do
                    const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn,
                    int alph, int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std,
                    double *out_alpha, double *out_alpha_std, double *out_chi2, int32_t *status);
+
+/* Row-sharded form for the multi-GPU inversion (cells shard by grid rows): the input
+ * maps hold only grid rows [row0, row0+nrows) of a grid with ny_total rows -- (nx, nrows, ns) maps and
+ * (nx, nrows) wd / rhoc / zc / mask -- and the call fits exactly the cells Project.estimate_grid
+ * (classes.py:1218-1219) would visit inside that row range.  Outputs are (nx/nn, out_rows) maps
+ * holding global output rows [first_out_row, first_out_row + out_rows) as given by
+ * pfx_l2_fit_rows_shape; concatenating the shards' outputs along y gives the full-grid maps.
+ * pfx_l2_fit_dev is this call with row0 = 0 and nrows = ny_total. */
+int pfx_l2_fit_rows_shape(int ny_total, int row0, int nrows, int nn, int *first_out_row, int *out_rows);
+int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, const double *k_dev, int ns, int nx,
+                        int ny_total, int row0, int nrows, const double *wl_admit, const double *ewl_admit,
+                        const double *wl_coh, const double *ewl_coh, const double *wd, const double *rhoc_map,
+                        const double *zc_map, const uint8_t *mask, int nn, int alph, int atype, double *out_te,
+                        double *out_te_std, double *out_f, double *out_f_std, double *out_alpha, double *out_alpha_std,
+                        double *out_chi2, int32_t *status);
 
 #ifdef __cplusplus
 }

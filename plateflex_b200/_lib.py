@@ -54,6 +54,8 @@ _SIGS = {
     "pfx_plan_info": ([_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_size_t)], _i),
     "pfx_plan_launch_count": ([_vp, C.POINTER(C.c_longlong)], _i),
     "pfx_plan_set_cutoff": ([_vp, _d], _i),
+    "pfx_plan_profile_enable": ([_vp, _i], _i),
+    "pfx_plan_profile_read": ([_vp, _vp, _vp, _i], _i),
     "pfx_wlet_transform_host": ([_vp, _vp, _i, _i, _vp], _i),
     "pfx_wlet_transform_dev": ([_vp, _vp, _i, _i, _vp], _i),
     "pfx_wlet_scalogram_host": ([_vp, _vp, _i, _i, _vp, _vp], _i),
@@ -67,6 +69,9 @@ _SIGS = {
     "pfx_cube_admit_coh_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pfx_flex_xspec_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pfx_l2_fit_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] + [_vp] * 8, _i),
+    "pfx_l2_fit_rows_shape": ([_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)], _i),
+    "pfx_l2_fit_rows_dev": ([_i, _vp, C.POINTER(FlexConf), _vp, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] +
+                            [_vp] * 8, _i),
     "pfx_l2_fit_dev": ([_i, _vp, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] + [_vp] * 8, _i),
 }
 for _name, (_args, _res) in _SIGS.items():
@@ -140,6 +145,18 @@ class Plan:
         n = C.c_longlong()
         check(lib.pfx_plan_launch_count(self.handle, C.byref(n)))
         return n.value
+
+    KERNEL_CLASSES = ("forward", "prepare", "pass1", "pass2", "reduce", "dense_mul", "dense_fft", "crop")
+
+    def profile(self, on=True):
+        check(lib.pfx_plan_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{kernel class: (milliseconds, launches)} since the last read (device timers, see the header)."""
+        n = len(self.KERNEL_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_longlong * n)()
+        check(lib.pfx_plan_profile_read(self.handle, ms, cnt, n))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.KERNEL_CLASSES) if cnt[i]}
 
     def key(self):
         return (self.nx, self.ny, self.dx, self.dy, self.k.tobytes(), self.k0, self.engine, self.device)

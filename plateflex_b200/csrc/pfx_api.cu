@@ -77,9 +77,24 @@ int pfx_plan::scratch(int slot, size_t bytes, void **p)
     return PFX_OK;
 }
 
+cudaEvent_t pfx_plan::prof_event()
+{
+    if (!spare_events.empty()) {
+        cudaEvent_t e = spare_events.back();
+        spare_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return e;
+}
+
 extern "C" {
 
-int pfx_version(void) { return 100; }
+int pfx_version(void) { return 101; }
 
 const char *pfx_last_error(void) { return g_err.c_str(); }
 
@@ -214,6 +229,11 @@ int pfx_plan_destroy(pfx_plan *pl)
         if (pl->ev_reduced[b]) cudaEventDestroy(pl->ev_reduced[b]);
     }
     if (pl->ev_join) cudaEventDestroy(pl->ev_join);
+    for (const PfxProfSpan &sp : pl->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (cudaEvent_t e : pl->spare_events) cudaEventDestroy(e);
     if (pl->fft_fwd_ok) cufftDestroy(pl->fft_fwd);
     for (int g = 0; g < 2; g++)
         if (pl->fft_inv_ok[g]) cufftDestroy(pl->fft_inv[g]);
@@ -244,6 +264,36 @@ int pfx_plan_launch_count(const pfx_plan *pl, long long *kernels)
 {
     PFX_ARG(pl && kernels, "null argument");
     *kernels = pl->launches;
+    return PFX_OK;
+}
+
+int pfx_plan_profile_enable(pfx_plan *pl, int on)
+{
+    PFX_ARG(pl, "plan is null");
+    pl->profiling = on != 0;
+    return PFX_OK;
+}
+
+int pfx_plan_profile_read(pfx_plan *pl, double *ms, long long *count, int n)
+{
+    PFX_ARG(pl && ms && count && n >= 1, "null argument");
+    DeviceGuard guard(pl->device);
+    for (int i = 0; i < n; i++) {
+        ms[i] = 0.0;
+        count[i] = 0;
+    }
+    for (const PfxProfSpan &sp : pl->spans) {
+        PFX_CUDA(cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        PFX_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+        if (sp.cls < n) {
+            ms[sp.cls] += (double)t;
+            count[sp.cls]++;
+        }
+        pl->spare_events.push_back(sp.a);
+        pl->spare_events.push_back(sp.b);
+    }
+    pl->spans.clear();
     return PFX_OK;
 }
 
@@ -313,10 +363,12 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
             PFX_CUDA(cudaStreamWaitEvent(red_stream, pl->ev_planes[b], 0));
         }
         if (mode == OUT_CUBE) {
+            ProfScope prof(pl, PFX_KC_CROP, red_stream);
             PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, red_stream));
         } else {
             double *o[4] = {nullptr, nullptr, nullptr, nullptr};
             for (int i = 0; i < nouts; i++) o[i] = d_outs[i] + so * elems[i];
+            ProfScope prof(pl, PFX_KC_REDUCE, red_stream);
             PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream));
         }
         pl->launches++;
@@ -398,7 +450,10 @@ int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, 
             PFX_CHECK(pruned_scale_planes(pl, is, 1));
             v = pruned_view(pl, 0);
         }
-        PFX_CHECK(launch_crop(pl->nx, pl->ny, v, reinterpret_cast<double2 *>(d_slab), pl->stream));
+        {
+            ProfScope prof(pl, PFX_KC_CROP, pl->stream);
+            PFX_CHECK(launch_crop(pl->nx, pl->ny, v, reinterpret_cast<double2 *>(d_slab), pl->stream));
+        }
         pl->launches++;
         PFX_CUDA(cudaMemcpyAsync(cube + (size_t)(is - is0) * slab, d_slab, slab * sizeof(double), cudaMemcpyDeviceToHost,
                                  pl->stream));

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256)
 int forward_spectrum(pfx_plan *pl, const double *grid_dev, int slot)
 {
     const size_t n = (size_t)pl->nx * pl->ny, P = (size_t)pl->NX * pl->NY;
+    ProfScope prof(pl, PFX_KC_FORWARD, pl->stream);
     sum_partial_kernel<<<SUM_BLOCKS, SUM_THREADS, 0, pl->stream>>>(grid_dev, n, pl->d_partial);
     sum_final_kernel<<<1, SUM_THREADS, 0, pl->stream>>>(pl->d_partial, SUM_BLOCKS, 1.0 / (double)n);
     double2 *xp = pl->d_spec[slot];
@@ -192,17 +193,21 @@ int dense_scale_planes(pfx_plan *pl, int is, int ngrids)
 {
     const PfxScaleConsts &c = pl->consts[is];
     dim3 tg((pl->NX + pl->NY + 255) / 256, PFX_NA);
-    dense_tables_kernel<<<tg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_kx, pl->d_ky, c, pl->d_tab);
-    dim3 mg((pl->NX + 255) / 256, pl->NY);
-    if (ngrids == 2)
-        dense_multiply_kernel<2><<<mg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_spec[0], pl->d_spec[1], pl->d_tab,
-                                                             pl->d_u2, pl->d_v2, c, pl->d_planes);
-    else
-        dense_multiply_kernel<1><<<mg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_spec[0], nullptr, pl->d_tab,
-                                                             pl->d_u2, pl->d_v2, c, pl->d_planes);
+    {
+        ProfScope prof(pl, PFX_KC_DENSE_MUL, pl->stream);
+        dense_tables_kernel<<<tg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_kx, pl->d_ky, c, pl->d_tab);
+        dim3 mg((pl->NX + 255) / 256, pl->NY);
+        if (ngrids == 2)
+            dense_multiply_kernel<2><<<mg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_spec[0], pl->d_spec[1],
+                                                                 pl->d_tab, pl->d_u2, pl->d_v2, c, pl->d_planes);
+        else
+            dense_multiply_kernel<1><<<mg, 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_spec[0], nullptr, pl->d_tab,
+                                                                 pl->d_u2, pl->d_v2, c, pl->d_planes);
+    }
     PFX_CUDA(cudaGetLastError());
     cufftHandle h = pl->fft_inv[ngrids - 1];
     PFX_CUFFT(cufftSetStream(h, pl->stream));
+    ProfScope prof(pl, PFX_KC_DENSE_FFT, pl->stream);
     PFX_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *)pl->d_planes, (cufftDoubleComplex *)pl->d_planes, CUFFT_INVERSE));
     pl->launches += 3;
     return PFX_OK;

@@ -323,6 +323,7 @@ int pruned_prepare(pfx_plan *pl, int ngrids)
 {
     PrunedState *st = state_of(pl);
     const size_t P = (size_t)pl->NX * pl->NY;
+    ProfScope prof(pl, PFX_KC_PREPARE, pl->stream);
     zmul_kernel<<<dim3((pl->NX + 255) / 256, pl->NY), 256, 0, pl->stream>>>(
         pl->NX, pl->NY, pl->d_spec[0], ngrids == 2 ? pl->d_spec[1] : nullptr, pl->d_u2, pl->d_v2, st->zplanes);
     PFX_CUDA(cudaGetLastError());
@@ -365,8 +366,14 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
     dim3 g1(std::min(sd.kamax, st->ctas_per_transform), PFX_NA * ngrids);
     dim3 g2(std::min(ngroups, st->ctas_per_transform), PFX_NA * ngrids);
-    PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
-    PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
+    {
+        ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
+        PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
+    }
+    {
+        ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
+        PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
+    }
     for (int ia = 0; ia < PFX_NA; ia++) st->cur_ce[ia] = sd.ce[ia];
     pl->launches += 2;
     return PFX_OK;

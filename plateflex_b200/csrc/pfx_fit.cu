@@ -42,6 +42,8 @@ struct FitArgs {
     int nn, atype;
     int fx, fy;  // number of fitted cells along x, y: len(range(0, nx-nn, nn))
     int mx, my;  // output map shape (nx/nn, ny/nn)
+    int row0;    // global index of the first grid row (y) held by the maps (row-sharded fits; else 0)
+    int cj0;     // global index of the first output row of this shard (else 0)
     double *o_te, *o_te_std, *o_f, *o_f_std, *o_a, *o_a_std, *o_chi2;
     int32_t *status;
 };
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(FIT_NT, FIT_MIN_BLOCKS) fit_cell_kernel(FitArg
     const int tid = threadIdx.x;
     for (long long cell = (long long)blockIdx.x * FIT_NT + tid; cell < ncells; cell += (long long)gridDim.x * FIT_NT) {
         const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
-        const size_t src = (size_t)(cj * a.nn) * a.nx + (size_t)ci * a.nn;
+        const size_t src = (size_t)((a.cj0 + cj) * a.nn - a.row0) * a.nx + (size_t)ci * a.nn;
         const size_t dst = (size_t)cj * a.mx + ci;
         if (a.mask && a.mask[src]) continue;  // classes.py:1228-1231 (outputs stay zero)
         const double rhoc = a.rhoc_map ? a.rhoc_map[src] : a.conf.rhoc;  // classes.py:1087-1091
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
 
     for (long long cell = group; cell < ncells; cell += ngroups) {
         const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
-        const int i = ci * a.nn, j = cj * a.nn;
+        const int i = ci * a.nn, j = (a.cj0 + cj) * a.nn - a.row0;
         const size_t src = (size_t)j * a.nx + i;
         const size_t dst = (size_t)cj * a.mx + ci;
         if (a.mask && a.mask[src]) continue;  // classes.py:1228-1231 (outputs stay zero)
@@ -891,12 +893,37 @@ using namespace pfx;
 
 extern "C" {
 
+int pfx_l2_fit_rows_shape(int ny_total, int row0, int nrows, int nn, int *first_out_row, int *out_rows)
+{
+    PFX_ARG(ny_total >= 1 && row0 >= 0 && nrows >= 0 && row0 + nrows <= ny_total && nn >= 1, "bad row range");
+    const int cj0 = (row0 + nn - 1) / nn;
+    int cj1 = (row0 + nrows + nn - 1) / nn;  // first output row whose grid row lies beyond this shard
+    if (cj1 > ny_total / nn) cj1 = ny_total / nn;
+    if (first_out_row) *first_out_row = cj0;
+    if (out_rows) *out_rows = cj1 > cj0 ? cj1 - cj0 : 0;
+    return PFX_OK;
+}
+
 int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const double *k_dev, int ns, int nx, int ny,
                    const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,
                    const double *wd, const double *rhoc_map, const double *zc_map, const uint8_t *mask, int nn, int alph,
                    int atype, double *out_te, double *out_te_std, double *out_f, double *out_f_std, double *out_alpha,
                    double *out_alpha_std, double *out_chi2, int32_t *status)
 {
+    return pfx_l2_fit_rows_dev(device, stream, conf, k_dev, ns, nx, ny, 0, ny, wl_admit, ewl_admit, wl_coh, ewl_coh, wd,
+                               rhoc_map, zc_map, mask, nn, alph, atype, out_te, out_te_std, out_f, out_f_std, out_alpha,
+                               out_alpha_std, out_chi2, status);
+}
+
+int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, const double *k_dev, int ns, int nx,
+                        int ny_total, int row0, int nrows, const double *wl_admit, const double *ewl_admit,
+                        const double *wl_coh, const double *ewl_coh, const double *wd, const double *rhoc_map,
+                        const double *zc_map, const uint8_t *mask, int nn, int alph, int atype, double *out_te,
+                        double *out_te_std, double *out_f, double *out_f_std, double *out_alpha, double *out_alpha_std,
+                        double *out_chi2, int32_t *status)
+{
+    const int ny = nrows;
+    PFX_ARG(ny_total >= 1 && row0 >= 0 && nrows >= 1 && row0 + nrows <= ny_total, "bad row range");
     PFX_ARG(conf && k_dev, "conf or k is null");
     PFX_ARG(ns >= 1 && ns <= 64, "ns must be in [1, 64]");
     PFX_ARG(nx >= 1 && ny >= 1 && nn >= 1, "bad grid shape or decimator");
@@ -928,9 +955,14 @@ int pfx_l2_fit_dev(int device, void *stream, const pfx_flex_conf *conf, const do
     a.nn = nn;
     a.atype = atype;
     a.fx = (nx > nn) ? (nx - nn + nn - 1) / nn : 0;  // len(range(0, nx-nn, nn)), classes.py:1218
-    a.fy = (ny > nn) ? (ny - nn + nn - 1) / nn : 0;
     a.mx = nx / nn;                                  // classes.py:1189
-    a.my = ny / nn;
+    a.row0 = row0;
+    pfx_l2_fit_rows_shape(ny_total, row0, nrows, nn, &a.cj0, &a.my);
+    {
+        const int fy_total = (ny_total > nn) ? (ny_total - nn + nn - 1) / nn : 0;  // fitted output rows of the grid
+        const int hi = (a.cj0 + a.my < fy_total) ? a.cj0 + a.my : fy_total;
+        a.fy = hi > a.cj0 ? hi - a.cj0 : 0;
+    }
     a.o_te = out_te;
     a.o_te_std = out_te_std;
     a.o_f = out_f;

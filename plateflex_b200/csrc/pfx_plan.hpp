@@ -13,6 +13,24 @@ struct PfxScaleConsts {
     double e0[PFX_NA];     // exp(-0.5*(kx0^2 + ky0^2))
 };
 
+// Kernel classes of the per-kernel device timers (pfx_plan_profile_*).
+enum PfxKernelClass {
+    PFX_KC_FORWARD = 0,  // mean + mirror/pad + forward cuFFT, per grid
+    PFX_KC_PREPARE,      // admissibility transform Z (pruned engine), per call
+    PFX_KC_PASS1,        // pruned engine, y-direction transforms of one scale
+    PFX_KC_PASS2,        // pruned engine, x-direction transforms of one scale
+    PFX_KC_REDUCE,       // azimuth reduction + jackknife of one scale
+    PFX_KC_DENSE_MUL,    // dense engine: tables + daughter multiply of one scale
+    PFX_KC_DENSE_FFT,    // dense engine: batched inverse cuFFT of one scale
+    PFX_KC_CROP,         // wl_trans materialiser of one scale
+    PFX_KC_COUNT
+};
+
+struct PfxProfSpan {
+    int cls;
+    cudaEvent_t a, b;
+};
+
 struct pfx_plan {
     int nx = 0, ny = 0, ns = 0, NX = 0, NY = 0;
     int engine = PFX_ENGINE_PRUNED, device = 0;
@@ -54,11 +72,41 @@ struct pfx_plan {
 
     std::vector<void *> owned;  // everything to cudaFree on destroy
 
+    // optional per-kernel device timers: an event pair around every launch of a class, on the stream
+    // the kernel is launched on; read back (after a synchronise) by pfx_plan_profile_read
+    bool profiling = false;
+    std::vector<PfxProfSpan> spans;
+    std::vector<cudaEvent_t> spare_events;
+    cudaEvent_t prof_event();
+
     int alloc(void **p, size_t bytes);
     int scratch(int slot, size_t bytes, void **p);
 };
 
 namespace pfx {
+
+// RAII event pair around the launches of one kernel class (no-op unless plan->profiling).
+struct ProfScope {
+    pfx_plan *pl;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    ProfScope(pfx_plan *p, int cls, cudaStream_t s) : pl(p), st(s)
+    {
+        if (!pl->profiling) return;
+        cudaEvent_t a = pl->prof_event();
+        b = pl->prof_event();
+        if (!a || !b) {
+            b = nullptr;
+            return;
+        }
+        cudaEventRecord(a, st);
+        pl->spans.push_back({cls, a, b});
+    }
+    ~ProfScope()
+    {
+        if (b) cudaEventRecord(b, st);
+    }
+};
 
 // K1: mirror + de-mean + zero-pad (cpwt.f90:100-116, cpwt_sub.f90:435-449) then one forward FFT
 // (cpwt.f90:122) of grid g (device pointer, C order) into plan->d_spec[slot].
