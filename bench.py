@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the PlateFlex hot path on B200.
 
-Workload (BASELINE.json configs[1]): synthetic 1024x1024 topography + Bouguer pair, 5 km
-spacing, ns = 20 scales (the first 20 of the grid's natural wavenumber ladder), 11 azimuths.
+Workload (default): BASELINE.json configs[1] -- synthetic 1024x1024 topography + Bouguer pair,
+5 km spacing, ns = 20 scales (the first 20 of the grid's natural wavenumber ladder), 11 azimuths.
 One step = one pass CWT -> admittance / coherence with jackknife errors for the pair:
 nx*ny*ns*11 = 2.31e8 grid-cell.scale.azimuth units, two grids in, four (nx,ny,ns) maps out.
+`--config C1|C3|C4|C5` selects the other BASELINE configurations (parity / sizing cases).
 
   value      units/s with the two input grids already resident in HBM (device-pointer C ABI)
   e2e        same metric through the host-pointer C ABI call (pinned host buffers, H2D of the
              two grids and D2H of the four maps inside the timed region)
-  roofline   algorithmic bytes (547 B/unit for the two-grid path) / measured time
-  fit        per-cell L2 (Te, F) fit of the resulting maps, cells/s (second metric of BASELINE.json)
+  roofline   the dominant kernel: algorithmic bytes per launch (SURVEY.md 8d split per kernel,
+             see DESIGN.md) / its average launch duration, from CUDA event pairs recorded around
+             every launch on its own stream inside the timed region (pfx_plan_profile_*)
+  fit        per-cell L2 (Te, F[, alpha]) fit of the resulting maps, cells/s (second metric)
   cpu_baseline  the CPU oracle port (reference precision, OpenMP over planes) on a bounded sample
 
 `--impl reference` times only the CPU oracle port (the reference's Fortran cannot be built here).
-Multi-GPU (torchrun): the scale axis is sharded over ranks, no data-path collective; the timed
-region is bracketed by barriers and the maximum over ranks is reported (strong scaling).
+
+Multi-GPU (torchrun, one rank per GPU):
+  --scaling weak   (default) every rank transforms its own grid pair (independent survey regions,
+                   no data-path collective); value = N * units / max-over-ranks time.
+  --scaling strong one grid pair, scales sharded over ranks, the four maps re-sharded by grid rows
+                   (NCCL all-to-all) for the cell-sharded fit; see plateflex_b200/sharding.py.
+The timed region is bracketed by barriers and the maximum over ranks is reported.
 """
 import argparse
 import ctypes as C
@@ -31,21 +39,51 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NX = NY = 1024
-DX = DY = 5.0
-NS = 20
 NA = 11
-BYTES_PER_UNIT = 2 * (4 * 64 + 16) + 4 * 8 / 11.0  # SURVEY.md 8d, two-grid admittance/coherence path
 METRIC = "grid-cell*scale*azimuth/s (CWT->admittance/coherence)"
 
+# BASELINE.json configs.  ns = 20 except C1 (the example grid's natural 19).
+CONFIGS = {
+    "C1": dict(nx=342, ny=341, dx=20.0169157785, dy=19.9970844654, ns=19, Te=30.0, F=0.5, ocean=None, boug=True,
+               alph=False, name="synthetic 342x341 example-shaped topo+Bouguer (BASELINE configs[0])"),
+    "C2": dict(nx=1024, ny=1024, dx=5.0, dy=5.0, ns=20, Te=40.0, F=0.5, ocean=None, boug=True, alph=False,
+               name="synthetic 1024x1024 topo+Bouguer, 5 km, ns=20, na=11 (BASELINE configs[1])"),
+    "C3": dict(nx=4096, ny=4096, dx=5.0, dy=5.0, ns=20, Te=40.0, F=0.5, ocean=None, boug=True, alph=False,
+               name="synthetic 4096x4096 land Bouguer, 5 km, ns=20 (BASELINE configs[2])"),
+    "C4": dict(nx=2048, ny=2048, dx=5.0, dy=5.0, ns=20, Te=20.0, F=0.2, ocean=4500.0, boug=False, alph=True,
+               name="synthetic 2048x2048 ocean free-air, alpha fitted, ns=20 (BASELINE configs[3])"),
+    "C5": dict(nx=8192, ny=8192, dx=5.0, dy=5.0, ns=20, Te=40.0, F=0.5, ocean=None, boug=True, alph=False,
+               name="synthetic 8192x8192 continental grid, ns=20 (BASELINE configs[4])"),
+}
 
-def workload(nx=NX, ny=NY, ns=NS):
+
+def npow2(n):
+    p = 2
+    while p < n:
+        p *= 2
+    return p
+
+
+def alg_bytes_per_unit(cfg):
+    """per cell.scale.azimuth, two grids: 2*(rho*64 + 16) + 4*8/11 with
+    rho = padded/cell ratio; split per kernel: each FFT pass 2*rho*32, the epilogue 2*16 + 32/11."""
+    rho = npow2(2 * cfg["nx"]) * npow2(2 * cfg["ny"]) / float(cfg["nx"] * cfg["ny"])
+    per = {"pass1": 2 * rho * 32.0, "pass2": 2 * rho * 32.0, "reduce": 2 * 16.0 + 4 * 8 / 11.0}
+    per["dense_fft"] = per["pass1"] + per["pass2"]
+    per["dense_mul"] = 0.0  # the daughter multiply is implementation overhead, not algorithmic (8d)
+    return sum(per[k] for k in ("pass1", "pass2", "reduce")), per
+
+
+def workload(cfg, seed_offset=0):
     import plateflex_b200 as pf
     from plateflex_b200 import classes, synthetic
     pf.set_conf_cpwt()
     pf.set_conf_flex()
-    topo, grav = synthetic.make_pair(nx, ny, DX, DY, seed=20240000 + nx, Te=40.0, F=0.5)
-    k = classes._lam2k(nx, ny, DX, DY)[1][:ns].copy()
+    nx, ny = cfg["nx"], cfg["ny"]
+    topo, grav = synthetic.make_pair(nx, ny, cfg["dx"], cfg["dy"], seed=20240000 + nx + seed_offset, Te=cfg["Te"],
+                                     F=cfg["F"], boug=cfg["boug"], ocean_depth=cfg["ocean"],
+                                     rhoc=2800. if cfg["ocean"] else 2700.)
+    k = classes._lam2k(nx, ny, cfg["dx"], cfg["dy"])[1][:cfg["ns"]].copy()
     return topo, grav, k, pf.cf_wt.k0
 
 
@@ -60,7 +98,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -94,40 +132,57 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference(topo, grav, k, k0, sample_scales, threads):
+def ncu_traffic(config, cls):
+    """DRAM bytes per launch of a kernel class from the committed ncu capture (profiles/traffic.json,
+    written by scripts/summarise_ncu.py from `ncu --metrics dram__bytes_*`), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(config, {}).get(cls)
+    except (ValueError, OSError):
+        return None
+
+
+def cpu_reference(cfg, topo, grav, k, k0, sample_scales, threads):
     """The CPU oracle port in the reference's precision (float32, radix-2 fourn) on `sample_scales`."""
     from oracle import oracle as ora
     ora.lib()
     ks = k[list(sample_scales)]
     t0 = time.perf_counter()
-    w1 = ora.wlet_transform(topo, DX, DY, ks, k0=k0, prec=32, nthreads=threads)
-    w2 = ora.wlet_transform(grav, DX, DY, ks, k0=k0, prec=32, nthreads=threads)
+    w1 = ora.wlet_transform(topo, cfg["dx"], cfg["dy"], ks, k0=k0, prec=32, nthreads=threads)
+    w2 = ora.wlet_transform(grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=32, nthreads=threads)
     ora.wlet_admit_coh(w1, w2, prec=32)
     dt = time.perf_counter() - t0
     units = topo.shape[0] * topo.shape[1] * NA * len(ks)
     return units / dt, dt, units
 
 
-def run_reference(args, rank):
+def cpu_sample_scales(cfg):
+    """Bounded CPU sample: first and last scale up to 2048^2-cell grids, one scale above."""
+    return [0, cfg["ns"] - 1] if cfg["nx"] * cfg["ny"] <= 2048 * 2048 else [cfg["ns"] // 2]
+
+
+def run_reference(args, cfg, rank):
     if rank != 0:
         return
-    topo, grav, k, k0 = workload()
+    topo, grav, k, k0 = workload(cfg)
     threads = os.cpu_count() or 1
-    sample = [0, NS - 1]
+    sample = cpu_sample_scales(cfg)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, units = cpu_reference(topo, grav, k, k0, sample, threads)
+        v, dt, units = cpu_reference(cfg, topo, grav, k, k0, sample, threads)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
-    what = f"scales {sample} of {NS} ({units:.3g} units per step), float32 oracle port of cpwt.f90, OpenMP over planes"
+    what = (f"scales {sample} of {cfg['ns']} ({units:.3g} units per step), float32 oracle port of cpwt.f90 "
+            f"(the Fortran is not buildable here), OpenMP over planes")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic {NX}x{NY} topo+Bouguer, {DX:g} km, ns={NS}, na={NA} (BASELINE configs[1])",
-                   "sample": what},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "sample": what},
         "cpu_baseline": {"value": value, "unit": "units/s", "cores": threads, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -139,47 +194,59 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--engine", default=os.environ.get("PLATEFLEX_B200_ENGINE", "pruned"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, cfg, rank)
 
     import torch
     import torch.distributed as dist
-    from plateflex_b200 import _lib
+    from plateflex_b200 import _lib, sharding
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    strong = args.scaling == "strong" and world > 1
+    nx, ny, ns = cfg["nx"], cfg["ny"], cfg["ns"]
+    nxy = nx * ny
 
-    topo, grav, k, k0 = workload()
+    # weak: every rank owns a different pair (seed + rank); strong: the same pair everywhere
+    topo, grav, k, k0 = workload(cfg, seed_offset=0 if (strong or world == 1) else 1000 * rank)
     engine = _lib.ENGINE_DENSE if args.engine == "dense" else _lib.ENGINE_PRUNED
-    plan = _lib.Plan(NX, NY, DX, DY, k, k0, engine=engine, device=local)
+    plan = _lib.Plan(nx, ny, cfg["dx"], cfg["dy"], k, k0, engine=engine, device=local)
     stream = torch.cuda.current_stream()
     plan.set_stream(stream.cuda_stream)
 
-    # strong scaling: contiguous block of scales per rank
-    per = [NS // world + (1 if r < NS % world else 0) for r in range(world)]
-    is0 = sum(per[:rank])
-    is1 = is0 + per[rank]
+    cost = plan.scale_cost() if strong else None
+    if strong:
+        is0, is1 = sharding.scale_range(ns, world, rank, cost)
+    else:
+        is0, is1 = 0, ns
     nsl = is1 - is0
-    nxy = NX * NY
 
     d_topo = torch.from_numpy(topo).to(dev)
     d_grav = torch.from_numpy(grav).to(dev)
     outs = [torch.empty(max(nsl, 1) * nxy, dtype=torch.float64, device=dev) for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
+    resharder = sharding.RowResharder(nx, ny, ns, world, rank, dev, cost=cost) if strong else None
+
     def step_dev():
         if nsl > 0:
             _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1,
                                                        *[o.data_ptr() for o in outs]))
+        if strong:  # the exchange step of the sharded pipeline: scale-major -> row shards holding all scales
+            resharder.exchange(outs)
 
     def barrier():
         if world > 1:
@@ -205,70 +272,122 @@ def main():
             times.append(e0.elapsed_time(e1))
         barrier()
     launches = plan.launch_count() - launches0
+    # Second timed loop, same steps, with the per-kernel device timers on: an event pair around every
+    # launch on its own stream; the plan serialises its internal streams meanwhile so that each pair
+    # times one kernel alone.  prof_ms is this loop's own step time (the denominator of the shares).
+    plan.profile(True)
+    plan.profile_read()
+    ptimes = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if nsl > 0:
+            _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1,
+                                                       *[o.data_ptr() for o in outs]))
+        e1.record(stream)
+        e1.synchronize()
+        ptimes.append(e0.elapsed_time(e1))
+    kern = plan.profile_read()  # {class: (ms total, launches)}
+    plan.profile(False)
+    prof_ms = float(np.mean(ptimes))
+    barrier()
     t = torch.tensor(times, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, per step
     ms_per_step = float(t.mean().item())
-    units = nxy * NS * NA
-    value = units / (ms_per_step * 1e-3)
+    units_rank = nxy * nsl * NA
+    units_job = nxy * ns * NA * (1 if (strong or world == 1) else world)
+    value = units_job / (ms_per_step * 1e-3)
 
     # ---- e2e: host-pointer C ABI with pinned buffers (H2D + D2H inside the timed region) ----
-    h_in = [torch.from_numpy(a).pin_memory() for a in (topo, grav)]
-    h_out = [torch.empty(max(nsl, 1) * nxy, dtype=torch.float64).pin_memory() for _ in range(4)]
+    e2e = None
+    if not args.no_e2e:
+        h_in = [torch.from_numpy(a).pin_memory() for a in (topo, grav)]
+        h_out = [torch.empty(max(nsl, 1) * nxy, dtype=torch.float64).pin_memory() for _ in range(4)]
 
-    def step_host():
-        if nsl > 0:
-            _lib.check(_lib.lib.pfx_wlet_admit_coh_host(plan.handle, h_in[0].data_ptr(), h_in[1].data_ptr(), is0, is1,
-                                                        *[o.data_ptr() for o in h_out]))
+        def step_host():
+            if nsl > 0:
+                _lib.check(_lib.lib.pfx_wlet_admit_coh_host(plan.handle, h_in[0].data_ptr(), h_in[1].data_ptr(), is0,
+                                                            is1, *[o.data_ptr() for o in h_out]))
 
-    for _ in range(2):
-        step_host()
-    barrier()
-    te = []
-    for _ in range(max(3, args.steps // 2)):
+        for _ in range(2):
+            step_host()
+        barrier()
+        te = []
+        for _ in range(max(3, args.steps // 2)):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            step_host()  # synchronous: returns after the D2H copies completed
+            te.append((time.perf_counter() - t0) * 1e3)
+        t2 = torch.tensor(te, dtype=torch.float64, device=dev)
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        step_host()  # synchronous: returns after the D2H copies completed
-        te.append((time.perf_counter() - t0) * 1e3)
-    t2 = torch.tensor(te, dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t2.mean().item())
-    e2e = {"value": units / (e2e_ms * 1e-3), "unit": "units/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": 2 * nxy * 8, "d2h_bytes_per_step": 4 * nxy * nsl * 8 * (world if world > 1 else 1)}
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.mean().item())
+        per_rank_out = torch.tensor([4 * nxy * nsl * 8], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(per_rank_out)
+        e2e = {"value": units_job / (e2e_ms * 1e-3), "unit": "units/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 2 * nxy * 8 * world, "d2h_bytes_per_step": int(per_rank_out.item()),
+               "api": "pfx_wlet_admit_coh_host (what Project.wlet_admit_coh calls), pinned host buffers"}
 
-    # ---- second metric: per-cell L2 fit over the maps this rank holds (full-ns maps only at N=1) ----
+    # ---- second metric: per-cell L2 fit of the maps (N=1: whole grid; strong: this rank's row shard) ----
     fit = None
-    if not args.no_fit and world == 1:
+    if not args.no_fit and (world == 1 or strong):
         from plateflex_b200.flex import conf_flex
+        conf_flex.boug = 1 if cfg["boug"] else 0
+        if cfg["ocean"]:
+            conf_flex.rhoc = 2800.
         conf = conf_flex.as_struct()
+        alph = 1 if cfg["alph"] else 0
         d_k = torch.from_numpy(k).to(dev)
-        d_wd = torch.zeros(nxy, dtype=torch.float64, device=dev)
-        fo = [torch.empty(nxy, dtype=torch.float64, device=dev) for _ in range(5)]
-        st = torch.empty(nxy, dtype=torch.int32, device=dev)
+        wd_full = np.asfortranarray(-np.minimum(topo, 0.0))  # TopoGrid.water_depth, classes.py:533-536
+        if strong:
+            row0, nrows = resharder.row0, resharder.nrows
+            maps = resharder.local_maps()
+        else:
+            row0, nrows = 0, ny
+            maps = outs
+        d_wd = torch.from_numpy(np.ascontiguousarray(wd_full.T[row0:row0 + nrows])).to(dev).reshape(-1)
+        cj0, myl = C.c_int(), C.c_int()
+        _lib.check(_lib.lib.pfx_l2_fit_rows_shape(ny, row0, nrows, 1, C.byref(cj0), C.byref(myl)))
+        nout = max(nx * myl.value, 1)
+        fo = [torch.empty(nout, dtype=torch.float64, device=dev) for _ in range(7)]
+        st = torch.empty(nout, dtype=torch.int32, device=dev)
 
         def step_fit():
-            _lib.check(_lib.lib.pfx_l2_fit_dev(local, stream.cuda_stream, C.byref(conf), d_k.data_ptr(), NS, NX, NY,
-                                               *[o.data_ptr() for o in outs], d_wd.data_ptr(), None, None, None, 1, 0,
-                                               _lib.ATYPES["joint"], fo[0].data_ptr(), fo[1].data_ptr(),
-                                               fo[2].data_ptr(), fo[3].data_ptr(), None, None, fo[4].data_ptr(),
-                                               st.data_ptr()))
+            if nrows > 0:
+                _lib.check(_lib.lib.pfx_l2_fit_rows_dev(
+                    local, stream.cuda_stream, C.byref(conf), d_k.data_ptr(), ns, nx, ny, row0, nrows,
+                    *[o.data_ptr() for o in maps], d_wd.data_ptr(), None, None, None, 1, alph, _lib.ATYPES["joint"],
+                    fo[0].data_ptr(), fo[1].data_ptr(), fo[2].data_ptr(), fo[3].data_ptr(),
+                    fo[4].data_ptr() if alph else None, fo[5].data_ptr() if alph else None, fo[6].data_ptr(),
+                    st.data_ptr()))
         step_fit()
-        torch.cuda.synchronize()
+        barrier()
         ft = []
         for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
             e0.record(stream)
             step_fit()
             e1.record(stream)
             e1.synchronize()
             ft.append(e0.elapsed_time(e1))
-        cells = (NX - 1) * (NY - 1)
-        te_map = fo[0].cpu().numpy().reshape(NY, NX)[:-1, :-1]
-        fit = {"cells_per_s": cells / (np.mean(ft) * 1e-3), "ms": float(np.mean(ft)), "cells": cells, "atype": "joint",
-               "alph": False, "converged_frac": float((st.cpu().numpy() == 1).sum() / cells),
-               "median_Te_km": float(np.median(te_map)), "true_Te_km": 40.0}
+        tf = torch.tensor(ft, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        cells = (nx - 1) * (ny - 1)
+        fit_ms = float(tf.mean().item())
+        te_map = fo[0][:nx * myl.value].cpu().numpy().reshape(myl.value, nx)
+        stat = st[:nx * myl.value].cpu().numpy().reshape(myl.value, nx)
+        fitted = stat > 0
+        fit = {"cells_per_s": cells / (fit_ms * 1e-3), "ms": fit_ms, "cells": cells, "atype": "joint",
+               "alph": bool(alph), "converged_frac": float((stat == 1).sum() / max(fitted.sum(), 1)),
+               "median_Te_km": float(np.median(te_map[fitted])) if fitted.any() else None, "true_Te_km": cfg["Te"],
+               "sharding": f"rows over {world} rank(s)" if strong else "none"}
 
     if rank != 0:
         if world > 1:
@@ -276,25 +395,42 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    achieved = BYTES_PER_UNIT * units / (ms_per_step * 1e-3) / 1e9 / world  # per GPU
+    alg_total, alg = alg_bytes_per_unit(cfg)
+    # dominant kernel class by device time inside the timed region
+    dom = max((c for c in kern if c in alg), key=lambda c: kern[c][0], default=None)
+    kernels = {c: {"ms_per_step": kern[c][0] / args.steps, "launches_per_step": kern[c][1] / args.steps,
+                   "avg_launch_us": 1e3 * kern[c][0] / kern[c][1]} for c in kern}
+    roof = None
+    if dom:
+        units_launch = nxy * NA  # one launch = one scale, all 11 azimuths of both grids
+        avg_s = kern[dom][0] / kern[dom][1] * 1e-3
+        achieved = alg[dom] * units_launch / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(args.config, dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom] * units_launch, "avg_launch_us": avg_s * 1e6,
+                "share_of_step": kern[dom][0] / args.steps / prof_ms, "serialised_step_ms": prof_ms,
+                "whole_step": {"achieved": alg_total * units_rank / (ms_per_step * 1e-3) / 1e9,
+                               "frac": alg_total * units_rank / (ms_per_step * 1e-3) / 1e9 / peak,
+                               "bytes_per_unit": alg_total},
+                "note": ("algorithmic bytes of a dense 2-pass FP64 FFT path (SURVEY.md 8d); the band-pruned engine "
+                         "moves fewer bytes, so frac > 1 is possible; traffic = measured DRAM bytes per launch (ncu)")}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        v, dt, u = cpu_reference(topo, grav, k, k0, [0, NS - 1], threads)
+        sample = cpu_sample_scales(cfg)
+        v, dt, u = cpu_reference(cfg, topo, grav, k, k0, sample, threads)
         cpu = {"value": v, "unit": "units/s", "cores": threads, "kind": "port",
-               "sample": f"scales [0, {NS - 1}] of {NS} ({u:.3g} units, {dt:.1f} s), float32 oracle port, OpenMP over planes"}
+               "sample": f"scales {sample} of {ns} ({u:.3g} units, {dt:.1f} s), float32 oracle port, OpenMP over planes"}
     line = {
         "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {NX}x{NY} topo+Bouguer, {DX:g} km, ns={NS}, na={NA} (BASELINE configs[1])",
-                   "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": f"scales over {world} rank(s)"},
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)",
+                   "sharding": (f"scales over {world} ranks + all-to-all to row shards" if strong else
+                                (f"{world} independent grid pairs, one per rank" if world > 1 else "single GPU"))},
         "clocks": clocks.summary(),
         "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "note": "whole step: algorithmic 547 B/unit x units / step time, per GPU"},
+        "roofline": roof, "kernels": kernels,
         "cpu_baseline": cpu, "fit": fit,
     }
     print(json.dumps(line))

@@ -99,9 +99,13 @@ int pfx_plan_set_stream(pfx_plan *plan, void *stream);
 int pfx_plan_info(const pfx_plan *plan, int *nnx, int *nny, size_t *device_bytes);
 /* number of kernels / library launches this plan has enqueued so far (for bench.py's gpu_launches). */
 int pfx_plan_launch_count(const pfx_plan *plan, long long *kernels);
+/* Relative cost estimate of each scale (cost[ns], arbitrary units): small scales have wide k-space
+ * supports and cost more.  Lets a multi-GPU caller cut the scale axis into balanced blocks. */
+int pfx_plan_scale_cost(const pfx_plan *plan, double *cost);
 /* Per-kernel device timers.  When enabled, every launch of the plan's kernels is bracketed by a CUDA
  * event pair on the stream it is launched on; pfx_plan_profile_read waits for the recorded spans,
- * returns the summed milliseconds and launch counts per kernel class and clears them.
+ * returns the summed milliseconds and launch counts per kernel class and clears them.  While enabled
+ * the plan does not overlap kernels on its internal streams, so each span times one kernel alone.
  * Classes (index): 0 forward spectrum, 1 admissibility transform, 2 pruned pass 1 (y transforms),
  * 3 pruned pass 2 (x transforms), 4 azimuth reduction + jackknife, 5 dense daughter multiply,
  * 6 dense inverse cuFFT, 7 wl_trans crop. */

@@ -54,6 +54,7 @@ _SIGS = {
     "pfx_plan_info": ([_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_size_t)], _i),
     "pfx_plan_launch_count": ([_vp, C.POINTER(C.c_longlong)], _i),
     "pfx_plan_set_cutoff": ([_vp, _d], _i),
+    "pfx_plan_scale_cost": ([_vp, _vp], _i),
     "pfx_plan_profile_enable": ([_vp, _i], _i),
     "pfx_plan_profile_read": ([_vp, _vp, _vp, _i], _i),
     "pfx_wlet_transform_host": ([_vp, _vp, _i, _i, _vp], _i),
@@ -147,6 +148,11 @@ class Plan:
         return n.value
 
     KERNEL_CLASSES = ("forward", "prepare", "pass1", "pass2", "reduce", "dense_mul", "dense_fft", "crop")
+
+    def scale_cost(self):
+        cost = np.empty(self.ns)
+        check(lib.pfx_plan_scale_cost(self.handle, ptr(cost)))
+        return cost
 
     def profile(self, on=True):
         check(lib.pfx_plan_profile_enable(self.handle, int(bool(on))))

@@ -267,6 +267,14 @@ int pfx_plan_launch_count(const pfx_plan *pl, long long *kernels)
     return PFX_OK;
 }
 
+int pfx_plan_scale_cost(const pfx_plan *pl, double *cost)
+{
+    PFX_ARG(pl && cost, "null argument");
+    for (int is = 0; is < pl->ns; is++)
+        cost[is] = (pl->engine == PFX_ENGINE_PRUNED) ? pruned_scale_cost(pl, is) : 1.0;  // dense: every scale costs the same
+    return PFX_OK;
+}
+
 int pfx_plan_profile_enable(pfx_plan *pl, int on)
 {
     PFX_ARG(pl, "plan is null");
@@ -339,7 +347,8 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     if (pruned) PFX_CHECK(pruned_prepare(pl, ngrids));
     // With two plane buffers (pruned engine) the reduction of scale s overlaps the passes of scale s+1.
     const int nbuf = pruned ? pruned_num_buffers(pl) : 1;
-    const bool overlap = nbuf == 2 && mode != OUT_CUBE;
+    // (per-kernel timing serialises everything on the caller's stream so that event pairs time one kernel each)
+    const bool overlap = nbuf == 2 && mode != OUT_CUBE && !pl->profiling;
     cudaStream_t red_stream = overlap ? pl->s_aux : pl->stream;
     for (int is = is0; is < is1; is++) {
         const int b = (is - is0) & 1;

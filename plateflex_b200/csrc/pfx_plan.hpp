@@ -127,6 +127,7 @@ int pruned_prepare(pfx_plan *pl, int ngrids);          // admissibility transfor
 int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);  // -> compact W planes of scale `is`
 PlaneView pruned_view(const pfx_plan *pl, int g);
 int pruned_num_buffers(const pfx_plan *pl);
+double pruned_scale_cost(const pfx_plan *pl, int is);
 void pruned_select_buffer(pfx_plan *pl, int b);
 
 }  // namespace pfx

@@ -79,12 +79,45 @@ def full_summary(tag):
                         f.write(f"   {m:75s} {r[i]:>16s} {units[i]}\n")
 
 
+def traffic_summary(tag, config="C2"):
+    """gpurun_out/traffic.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+    over the pass / reduce / fit launches of one step) -> profiles/traffic.json, the per-launch DRAM bytes
+    bench.py reports as roofline.traffic."""
+    import json
+    src = os.path.join(OUT, "traffic.csv")
+    if not os.path.exists(src):
+        return
+    rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
+    acc = collections.defaultdict(lambda: collections.defaultdict(float))
+    n = collections.Counter()
+    for r in rows:
+        name = r["Kernel Name"]
+        cls = next((c for c, pat in (("pass1", "pass1"), ("pass2", "pass2"), ("reduce", "reduce_kernel"),
+                                     ("fit", "fit_cell")) if pat in name), None)
+        if cls is None:
+            continue
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3}.get(r["Metric Unit"], 1)
+        acc[cls][r["Metric Name"]] += float(r["Metric Value"]) * mult
+        n[cls] += r["Metric Name"] == "gpu__time_duration.sum"
+    path = os.path.join(PROF, "traffic.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[config] = {c: (acc[c]["dram__bytes_read.sum"] + acc[c]["dram__bytes_write.sum"]) / n[c] for c in acc}
+    data[config + "_detail"] = {c: {"launches": n[c], "read_bytes_per_launch": acc[c]["dram__bytes_read.sum"] / n[c],
+                                    "write_bytes_per_launch": acc[c]["dram__bytes_write.sum"] / n[c],
+                                    "avg_launch_us_under_ncu": acc[c]["gpu__time_duration.sum"] / n[c],
+                                    "capture": tag} for c in acc}
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    shutil.copy(src, os.path.join(PROF, f"{tag}_traffic.csv"))
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launch_summary(tag)
     full_summary(tag)
-    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "smoke.log"):
+    traffic_summary(tag)
+    for name in ("bench.log", "bench_ref.log", "pytest_gpu.log", "smoke.log", "bench_C1.log", "bench_C3.log",
+                 "bench_C4.log", "bench_C5.log"):
         p = os.path.join(OUT, name)
         if os.path.exists(p):
             with open(p) as src, open(os.path.join(PROF, f"{tag}_{name}"), "w") as dst:

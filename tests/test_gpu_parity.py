@@ -298,3 +298,55 @@ def test_dense_and_pruned_engines_agree_at_full_size(pf, monkeypatch):
     _lib.clear_plans()
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), res["pruned"], res["dense"]):
         assert_maps_close(a, b, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nn,world,alph", [(1, 3, False), (3, 4, True), (7, 2, False)])
+def test_row_sharded_fit_equals_full_grid_fit(pf, nn, world, alph):
+    """pfx_l2_fit_rows_dev on row shards (the multi-GPU cell sharding, emulated on one device) must
+    reproduce the single-call grid fit bit for bit, decimation and unfitted last row included."""
+    import ctypes as C
+    import torch
+    from plateflex_b200 import _lib, estimate, sharding, synthetic
+    from plateflex_b200.cpwt import fused
+    from plateflex_b200.flex import conf_flex
+    pf.set_conf_flex()
+    nx, ny, dx, dy = 45, 38, 20.0, 20.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240011, Te=30.0, F=0.4)
+    k = np.array([1.0e-5, 1.6e-5, 2.5e-5, 4.0e-5, 6.0e-5, 9.0e-5])
+    maps = fused.wlet_admit_coh(topo, grav, dx, dy, k)
+    wd = np.asfortranarray(np.abs(np.random.default_rng(3).standard_normal((nx, ny))) * 50.0)
+    full = estimate.L2_estimate_grid(k, *maps, wd, nn=nn, alph=alph, atype="joint")
+    names = ["mean_Te", "std_Te", "mean_F", "std_F"] + (["mean_a", "std_a"] if alph else []) + ["chi2"]
+    dev = torch.device("cuda", _lib.default_device())
+    conf = conf_flex.as_struct()
+    d_k = torch.from_numpy(k).to(dev)
+    mx = nx // nn
+    pieces = {n: [] for n in names + ["status"]}
+    for r in range(world):
+        row0, row1 = sharding.row_range(ny, world, r)
+        nrows = row1 - row0
+        if nrows == 0:
+            continue
+        cj0, myl = C.c_int(), C.c_int()
+        _lib.check(_lib.lib.pfx_l2_fit_rows_shape(ny, row0, nrows, nn, C.byref(cj0), C.byref(myl)))
+        # (nx, nrows, ns) Fortran-ordered shard == C-ordered [s][j][i]
+        sh = [torch.from_numpy(np.ascontiguousarray(np.transpose(m, (2, 1, 0))[:, row0:row1, :])).to(dev) for m in maps]
+        d_wd = torch.from_numpy(np.ascontiguousarray(wd.T[row0:row1])).to(dev)
+        o = [torch.full((max(mx * myl.value, 1),), -7.0, dtype=torch.float64, device=dev) for _ in range(7)]
+        st = torch.full((max(mx * myl.value, 1),), -7, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib.pfx_l2_fit_rows_dev(
+            dev.index, None, C.byref(conf), d_k.data_ptr(), len(k), nx, ny, row0, nrows, *[t.data_ptr() for t in sh],
+            d_wd.data_ptr(), None, None, None, nn, int(alph), _lib.ATYPES["joint"], o[0].data_ptr(), o[1].data_ptr(),
+            o[2].data_ptr(), o[3].data_ptr(), o[4].data_ptr() if alph else None, o[5].data_ptr() if alph else None,
+            o[6].data_ptr(), st.data_ptr()))
+        torch.cuda.synchronize()
+        idx = {"mean_Te": 0, "std_Te": 1, "mean_F": 2, "std_F": 3, "mean_a": 4, "std_a": 5, "chi2": 6}
+        for n in names:
+            pieces[n].append(o[idx[n]][:mx * myl.value].cpu().numpy().reshape(myl.value, mx))
+        pieces["status"].append(st[:mx * myl.value].cpu().numpy().reshape(myl.value, mx))
+    for n in names + ["status"]:
+        got = np.concatenate(pieces[n], axis=0).T  # (mx, my)
+        assert got.shape == full[n].shape, (n, got.shape, full[n].shape)
+        assert np.array_equal(got, full[n], equal_nan=True), n
+    assert (full["status"] == 1).sum() > 0
