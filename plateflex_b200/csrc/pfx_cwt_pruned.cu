@@ -24,9 +24,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "pfx_plan.hpp"
 #include "pfx_pruned.hpp"
+#include "pfx_pruned_v2.cuh"
 
 namespace pfx {
 
@@ -141,6 +143,9 @@ struct PrunedState {
     size_t smem1 = 0, smem2 = 0;
     int cpc = 2;
     int ctas_per_transform = 128;
+    // second-generation kernels (pfx_pruned_v2.cuh), chosen per scale and axis: variant < 0 = first generation
+    std::vector<int> v2x, v2y, v2x_ctas, v2y_ctas;
+    int nsm = 148;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
     std::vector<std::pair<void *, size_t>> owned;
 };
@@ -173,14 +178,36 @@ int plan_init_pruned(pfx_plan *pl)
     const size_t P = (size_t)NX * NY;
     int dev_smem = 0;
     PFX_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, pl->device));
-    const size_t budget = (size_t)dev_smem;
+    size_t budget = (size_t)dev_smem;
 
     st->cpc = (NX <= 4096) ? 2 : 1;
+    {
+        const char *b = getenv("PLATEFLEX_B200_SMEM_BUDGET");  // experiment knob: shared memory per CTA, bytes
+        if (b && atol(b) > 0) budget = std::min(budget, (size_t)atol(b));
+        const char *c2 = getenv("PLATEFLEX_B200_CPC");
+        if (c2 && (atoi(c2) == 1 || atoi(c2) == 2)) st->cpc = atoi(c2);
+    }
     {
         const char *c = getenv("PLATEFLEX_B200_CTAS");
         if (c && atoi(c) > 0) st->ctas_per_transform = atoi(c);
     }
     st->sd.resize(ns);
+    st->v2x.assign(ns, -1);
+    st->v2y.assign(ns, -1);
+    st->v2x_ctas.assign(ns, 0);
+    st->v2y_ctas.assign(ns, 0);
+    PFX_CUDA(cudaDeviceGetAttribute(&st->nsm, cudaDevAttrMultiProcessorCount, pl->device));
+    // PLATEFLEX_B200_V2 = "off" | "<lines per CTA 1|2>,<prefetch 0|1>"  (default "1,0")
+    bool v2_on = true;
+    int v2_cpc = 1, v2_pre = 0;
+    {
+        const char *e = getenv("PLATEFLEX_B200_V2");
+        if (e && !strcmp(e, "off")) v2_on = false;
+        else if (e && strlen(e) >= 3) {
+            v2_cpc = (e[0] == '2') ? 2 : 1;
+            v2_pre = (e[2] == '1') ? 1 : 0;
+        }
+    }
     size_t tabu_n = 0, tabv_n = 0, twa_n = 0, twb_n = 0, kamax_all = 0;
     std::vector<int> h_lo((size_t)ns * 4 * PFX_NA);
     for (int is = 0; is < ns; is++) {
@@ -204,6 +231,24 @@ int plan_init_pruned(pfx_plan *pl)
         }
         plan_axis(sd.ax, NX, std::max(kamax, 1), nx, budget, st->cpc);
         plan_axis(sd.ay, NY, std::max(kbmax, 1), ny, budget, 1);
+        // second-generation kernels: padded axis of at least 2048 samples and 32 <= L <= 2048
+        auto pick_v2 = [&](AxisDesc &A, int cpc, int pre) -> int {
+            if (!v2_on || A.N < 2048 || A.logL > 11) return -1;
+            if (A.logL < 5) {
+                A.L = 32;
+                A.logL = 5;
+                A.r = A.N / A.L;
+                A.logr = A.logN - A.logL;
+                A.rc = A.r;
+                A.logrc = A.logr;
+                A.pad = 0;
+            }
+            const int multi = A.N > 2048;
+            if (multi || pre) cpc = 1;
+            return cpc | (pre << 4) | (multi << 5);
+        };
+        st->v2x[is] = pick_v2(sd.ax, v2_cpc, v2_pre);
+        st->v2y[is] = pick_v2(sd.ay, v2_cpc, v2_pre);
         sd.kamax = std::max(kamax, 1);
         sd.tabu = tabu_n;
         sd.tabv = tabv_n;
@@ -214,8 +259,8 @@ int plan_init_pruned(pfx_plan *pl)
         twa_n += (size_t)PFX_NA * NX;
         twb_n += (size_t)PFX_NA * NY;
         kamax_all = std::max(kamax_all, (size_t)sd.kamax);
-        st->smem1 = std::max(st->smem1, prn_smem_bytes(sd.ay, 1));
-        st->smem2 = std::max(st->smem2, prn_smem_bytes(sd.ax, st->cpc));
+        if (st->v2y[is] < 0) st->smem1 = std::max(st->smem1, prn_smem_bytes(sd.ay, 1));
+        if (st->v2x[is] < 0) st->smem2 = std::max(st->smem2, prn_smem_bytes(sd.ax, st->cpc));
     }
     if (st->smem1 > (size_t)dev_smem || st->smem2 > (size_t)dev_smem) {
         set_error("pruned engine: a %d x %d padded line does not fit in shared memory; use the dense engine", NX, NY);
@@ -297,8 +342,19 @@ int plan_init_pruned(pfx_plan *pl)
 
     for (int is = 0; is < ns; is++) {
         const ScaleDesc &sd = st->sd[is];
-        PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
-        PFX_CHECK(prn_configure_pass2(sd.ax.logL, sd.ax.pad, st->cpc, st->smem2));
+        int res = 0;
+        if (st->v2y[is] >= 0) {
+            PFX_CHECK(v2_configure_p1(sd.ay.logL, st->v2y[is], &res));
+            st->v2y_ctas[is] = std::max(res, 1) * st->nsm;
+        } else {
+            PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
+        }
+        if (st->v2x[is] >= 0) {
+            PFX_CHECK(v2_configure_p2(sd.ax.logL, st->v2x[is], &res));
+            st->v2x_ctas[is] = std::max(res, 1) * st->nsm;
+        } else {
+            PFX_CHECK(prn_configure_pass2(sd.ax.logL, sd.ax.pad, st->cpc, st->smem2));
+        }
     }
     return PFX_OK;
 }
@@ -366,13 +422,31 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
     dim3 g1(std::min(sd.kamax, st->ctas_per_transform), PFX_NA * ngrids);
     dim3 g2(std::min(ngroups, st->ctas_per_transform), PFX_NA * ngrids);
+    const int ntr = PFX_NA * ngrids;
+    const char *ctas_env = getenv("PLATEFLEX_B200_CTAS");
     {
         ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
-        PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
+        if (st->v2y[is] >= 0) {
+            v2::V2Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
+            const int cpc = st->v2y[is] & 15, groups = (sd.kamax + cpc - 1) / cpc;
+            // a few waves: the number of columns differs between azimuths
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v2y_ctas[is] / ntr);
+            PFX_CHECK(v2_launch_p1(va, sd.ay.logL, st->v2y[is], dim3(std::min(groups, ctas), ntr), pl->stream));
+        } else {
+            PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
+        }
     }
     {
         ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
-        PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
+        if (st->v2x[is] >= 0) {
+            v2::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
+            const int cpc = st->v2x[is] & 15, groups = (pl->ny + cpc - 1) / cpc;
+            // one wave of persistent CTAs: every transform has the same number of rows
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v2x_ctas[is] / ntr);
+            PFX_CHECK(v2_launch_p2(va, sd.ax.logL, st->v2x[is], dim3(std::min(groups, ctas), ntr), pl->stream));
+        } else {
+            PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
+        }
     }
     for (int ia = 0; ia < PFX_NA; ia++) st->cur_ce[ia] = sd.ce[ia];
     pl->launches += 2;

@@ -28,7 +28,23 @@ CASES = [  # nx, ny, dx, dy, wavenumbers (rad/m)
     (17, 50, 20.0, 7.0, [1.5e-5, 6e-5]),
     (64, 48, 10.0, 10.0, None),  # natural wavenumber ladder of the grid (classes._lam2k)
     (2, 3, 10.0, 10.0, [5e-5]),
+    # padded axes of 2048 / 4096 / 8192 samples: the second-generation pruned kernels (pfx_pruned_v2.cuh),
+    # one part per line, two and four parts per line; natural ladders reach every FFT length up to N
+    (520, 24, 5.0, 5.0, None),
+    (24, 520, 5.0, 5.0, None),
+    (1030, 20, 5.0, 5.0, ("ladder", 2)),
+    (18, 2050, 5.0, 5.0, ("ladder", 4)),
 ]
+
+
+def _wavenumbers(kf, nx, ny, dx, dy):
+    """Explicit list, the grid's natural ladder (None), or every n-th scale of it (("ladder", n))."""
+    from plateflex_b200 import classes
+    if kf is None:
+        return classes._lam2k(nx, ny, dx, dy)[1]
+    if isinstance(kf, tuple):
+        return classes._lam2k(nx, ny, dx, dy)[1][::-1][::kf[1]][::-1].copy()
+    return np.array(kf)
 
 
 @pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES)
@@ -36,7 +52,7 @@ def test_wlet_transform_matches_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
     from plateflex_b200 import classes
     from plateflex_b200.cpwt import cpwt
     g = red_field(nx, ny, seed=nx * 100 + ny) * 400.0 + 37.0
-    kf = np.array(kf) if kf is not None else classes._lam2k(nx, ny, dx, dy)[1]
+    kf = _wavenumbers(kf, nx, ny, dx, dy)
     got = cpwt.wlet_transform(g, dx, dy, kf)
     ref = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0, prec=64)
     assert got.shape == ref.shape == (nx, ny, 11, len(kf)) and got.dtype == np.complex128
@@ -47,13 +63,13 @@ def test_wlet_transform_matches_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
         assert_maps_close(part(flat(got)), part(flat(ref)), "wl_trans", rtol=1e-9, atol_rel=1e-11)
 
 
-@pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[:4])
+@pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[:4] + CASES[5:7])
 def test_fused_reductions_match_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
     from plateflex_b200 import classes
     from plateflex_b200.cpwt import fused
     t = red_field(nx, ny, seed=1) * 500.0
     g = 0.08 * t + red_field(nx, ny, seed=2) * 20.0
-    kf = np.array(kf) if kf is not None else classes._lam2k(nx, ny, dx, dy)[1]
+    kf = _wavenumbers(kf, nx, ny, dx, dy)
     w1 = ora.wlet_transform(t, dx, dy, kf, k0=pf.cf_wt.k0)
     w2 = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0)
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), fused.wlet_admit_coh(t, g, dx, dy, kf),
