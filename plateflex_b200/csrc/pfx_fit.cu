@@ -604,23 +604,33 @@ constexpr int FIT_NT = 128;
 #define FIT_MIN_BLOCKS 3
 #endif
 
-template <int NP>
-__global__ void __launch_bounds__(FIT_NT, FIT_MIN_BLOCKS) fit_cell_kernel(FitArgs a)
+// CACHE: the cell's observations (value and 1/sigma per scale) are copied to shared memory once and every model
+// evaluation reads them from there instead of from L2 (4 x ns more doubles per thread, two CTAs per SM).
+template <int NP, bool CACHE>
+__global__ void __launch_bounds__(FIT_NT, CACHE ? 2 : FIT_MIN_BLOCKS) fit_cell_kernel(FitArgs a)
 {
     extern __shared__ double fsh[];
+    // Depth attenuation per (cell, scale), one array per thread: the deep term 2 pi G drho e^{-k(zc+wd)} for
+    // Bouguer data (the top term vanishes); for free air with one crustal thickness e^{-k wd}, from which both
+    // terms follow with the per-scale table e^{-k zc}; for free air with a zc grid both terms (two arrays).
+    const bool freeair = a.conf.boug != 1;
+    const bool two = freeair && a.zc_map != nullptr;  // both terms stored
+    const bool shared_zc = freeair && !two;           // e^{-k wd} stored
     double *k4 = fsh;                              // [ns] k^4 * Em*1e9/12/(1-nu^2)
-    double *sdeep = fsh + a.ns;                    // [ns][FIT_NT]
-    double *stop = sdeep + (size_t)a.ns * FIT_NT;  // [ns][FIT_NT] (free-air only)
+    double *ezc = fsh + a.ns;                      // [ns] e^{-k zc}  (uniform zc)
+    double *sdeep = fsh + 2 * a.ns;                // [ns][FIT_NT]  e^{-k wd}, or the deep term with a zc grid
+    double *stop = sdeep + (size_t)a.ns * FIT_NT;  // [ns][FIT_NT]  (zc grid and free air only, else absent)
+    double *sobs = stop + (two ? (size_t)a.ns * FIT_NT : 0);  // CACHE: [4][ns][FIT_NT]
     for (int s = threadIdx.x; s < a.ns; s += FIT_NT) {
         const double k2 = a.k[s] * a.k[s];
         k4[s] = (k2 * k2) * (FLEX_EM * 1.e9 / 12. / (1. - FLEX_NU * FLEX_NU));
+        ezc[s] = exp(-a.k[s] * a.conf.zc);
     }
     __syncthreads();
     const long long ncells = (long long)a.fx * a.fy;
     const size_t nxy = (size_t)a.nx * a.ny;
     const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
     const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
-    const bool freeair = a.conf.boug != 1;
     const int tid = threadIdx.x;
     for (long long cell = (long long)blockIdx.x * FIT_NT + tid; cell < ncells; cell += (long long)gridDim.x * FIT_NT) {
         const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
@@ -632,23 +642,36 @@ __global__ void __launch_bounds__(FIT_NT, FIT_MIN_BLOCKS) fit_cell_kernel(FitArg
         const FlexCell fc = flex_cell(a.conf, rhoc, zc, a.wd[src]);
         bool bad = false;
         for (int s = 0; s < a.ns; s++) {
-            const FlexK q = flex_k(fc, a.k[s]);
-            sdeep[s * FIT_NT + tid] = q.deep;
-            if (freeair) stop[s * FIT_NT + tid] = q.top;
+            if (shared_zc) {
+                sdeep[s * FIT_NT + tid] = (fc.wd == 0.) ? 1. : exp(-a.k[s] * fc.wd);
+            } else {
+                const FlexK q = flex_k(fc, a.k[s]);
+                sdeep[s * FIT_NT + tid] = q.deep;
+                if (two) stop[s * FIT_NT + tid] = q.top;
+            }
             const size_t o = src + nxy * s;
             if (use_adm) {
                 const double y = __ldg(a.adm + o), e = __ldg(a.eadm + o);
                 bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                if (CACHE) {
+                    sobs[(0 * a.ns + s) * FIT_NT + tid] = y;
+                    sobs[(1 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                }
             }
             if (use_coh) {
                 const double y = __ldg(a.coh + o), e = __ldg(a.ecoh + o);
                 bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                if (CACHE) {
+                    sobs[(2 * a.ns + s) * FIT_NT + tid] = y;
+                    sobs[(3 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                }
             }
         }
         if (bad) {  // SciPy raises ValueError here; we flag the cell
             write_bad_cell(a, dst, NP == 3);
             continue;
         }
+        const double cdeep = 2. * FLEX_PI * FLEX_GC * fc.drho, ctop = 2. * FLEX_PI * FLEX_GC * (fc.A * fc.rcf);
         auto evaluate = [&](const double(&x)[NP], Normal<NP> &nm) {
             const double te = x[0], F = x[1];
             const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
@@ -663,21 +686,30 @@ __global__ void __launch_bounds__(FIT_NT, FIT_MIN_BLOCKS) fit_cell_kernel(FitArg
                 FlexK fk;
                 fk.k4d = k4[s];
                 fk.deep = sdeep[s * FIT_NT + tid];
-                fk.top = freeair ? stop[s * FIT_NT + tid] : 0.;
+                fk.top = 0.;
+                if (freeair) {
+                    if (two) {
+                        fk.top = stop[s * FIT_NT + tid];
+                    } else {
+                        fk.top = ctop * fk.deep;
+                        fk.deep = cdeep * (ezc[s] * fk.deep);
+                    }
+                }
                 double adm, coh, dA[3], dC[3];
                 flex_eval<true>(fc, fk, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
                 const size_t o = src + nxy * s;
                 if (use_adm) {
-                    const double w = rcp_nr(__ldg(a.eadm + o));  // curve_fit: transform = 1/sigma
-                    const double r = (adm - __ldg(a.adm + o)) * w;
+                    // curve_fit: transform = 1/sigma
+                    const double w = CACHE ? sobs[(1 * a.ns + s) * FIT_NT + tid] : rcp_nr(__ldg(a.eadm + o));
+                    const double r = (adm - (CACHE ? sobs[(0 * a.ns + s) * FIT_NT + tid] : __ldg(a.adm + o))) * w;
                     double jr[NP];
 #pragma unroll
                     for (int p = 0; p < NP; p++) jr[p] = dA[p] * w;
                     accumulate<NP>(acc, r, jr);
                 }
                 if (use_coh) {
-                    const double w = rcp_nr(__ldg(a.ecoh + o));
-                    const double r = (coh - __ldg(a.coh + o)) * w;
+                    const double w = CACHE ? sobs[(3 * a.ns + s) * FIT_NT + tid] : rcp_nr(__ldg(a.ecoh + o));
+                    const double r = (coh - (CACHE ? sobs[(2 * a.ns + s) * FIT_NT + tid] : __ldg(a.coh + o))) * w;
                     double jr[NP];
 #pragma unroll
                     for (int p = 0; p < NP; p++) jr[p] = dC[p] * w;
@@ -756,6 +788,7 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
         }
 
         // residuals r = (model - y)/sigma; accumulate cost, J^T r, J^T J over the group's scales
+        const double cdeep = 2. * FLEX_PI * FLEX_GC * fc.drho, ctop = 2. * FLEX_PI * FLEX_GC * (fc.A * fc.rcf);
         auto evaluate = [&](const double(&x)[NP], Normal<NP> &nm) {
             const double te = x[0], F = x[1];
             const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
@@ -869,18 +902,25 @@ int launch_fit_np(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 {
     const long long ncells = (long long)a.fx * a.fy;
-    const size_t smem = ((size_t)a.ns + 2 * (size_t)a.ns * FIT_NT) * sizeof(double);
+    const size_t smem0 =
+        (2 * (size_t)a.ns + ((a.zc_map && a.conf.boug != 1) ? 2 : 1) * (size_t)a.ns * FIT_NT) * sizeof(double);
+    const size_t smem1 = smem0 + 4 * (size_t)a.ns * FIT_NT * sizeof(double);
+    const char *ce = getenv("PLATEFLEX_B200_FIT_CACHE");
+    const bool cache = (ce ? atoi(ce) != 0 : true) && smem1 <= 113 * 1024;  // two CTAs per SM must still fit
+    const size_t smem = cache ? smem1 : smem0;
     long long blocks = (ncells + FIT_NT - 1) / FIT_NT;
     const long long cap = (long long)nsm * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (alph) {
-        PFX_CUDA(cudaFuncSetAttribute(fit_cell_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fit_cell_kernel<3><<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
-    } else {
-        PFX_CUDA(cudaFuncSetAttribute(fit_cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fit_cell_kernel<2><<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
-    }
+    auto launch = [&](auto kernel) -> int {
+        PFX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
+        return PFX_OK;
+    };
+    if (alph)
+        PFX_CHECK(cache ? launch(fit_cell_kernel<3, true>) : launch(fit_cell_kernel<3, false>));
+    else
+        PFX_CHECK(cache ? launch(fit_cell_kernel<2, true>) : launch(fit_cell_kernel<2, false>));
     PFX_CUDA(cudaGetLastError());
     return PFX_OK;
 }
