@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="strong scaling: epilogue stores into peer row shards over NVLink (p2p) or NCCL all-to-all")
     ap.add_argument("--engine", default=os.environ.get("PLATEFLEX_B200_ENGINE", "pruned"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true")
@@ -239,9 +241,14 @@ def main():
     outs = [torch.empty(max(nsl, 1) * nxy, dtype=torch.float64, device=dev) for _ in range(4)]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
-    resharder = sharding.RowResharder(nx, ny, ns, world, rank, dev, cost=cost) if strong else None
+    p2p = strong and args.exchange == "p2p"
+    resharder = sharding.RowResharder(nx, ny, ns, world, rank, dev, cost=cost) if (strong and not p2p) else None
+    peers = sharding.PeerShards(nx, ny, ns, world, rank, local) if p2p else None
 
     def step_dev():
+        if p2p:  # the epilogue of every scale stores its rows straight into the owners' shards (NVLink)
+            peers.transform(plan, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1)
+            return
         if nsl > 0:
             _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1,
                                                        *[o.data_ptr() for o in outs]))
@@ -343,12 +350,15 @@ def main():
         alph = 1 if cfg["alph"] else 0
         d_k = torch.from_numpy(k).to(dev)
         wd_full = np.asfortranarray(-np.minimum(topo, 0.0))  # TopoGrid.water_depth, classes.py:533-536
-        if strong:
+        if p2p:
+            row0, nrows = peers.row0, peers.nrows
+            map_ptrs = peers.local_map_ptrs()
+        elif strong:
             row0, nrows = resharder.row0, resharder.nrows
-            maps = resharder.local_maps()
+            map_ptrs = [o.data_ptr() for o in resharder.local_maps()]
         else:
             row0, nrows = 0, ny
-            maps = outs
+            map_ptrs = [o.data_ptr() for o in outs]
         d_wd = torch.from_numpy(np.ascontiguousarray(wd_full.T[row0:row0 + nrows])).to(dev).reshape(-1)
         cj0, myl = C.c_int(), C.c_int()
         _lib.check(_lib.lib.pfx_l2_fit_rows_shape(ny, row0, nrows, 1, C.byref(cj0), C.byref(myl)))
@@ -360,7 +370,7 @@ def main():
             if nrows > 0:
                 _lib.check(_lib.lib.pfx_l2_fit_rows_dev(
                     local, stream.cuda_stream, C.byref(conf), d_k.data_ptr(), ns, nx, ny, row0, nrows,
-                    *[o.data_ptr() for o in maps], d_wd.data_ptr(), None, None, None, 1, alph, _lib.ATYPES["joint"],
+                    *map_ptrs, d_wd.data_ptr(), None, None, None, 1, alph, _lib.ATYPES["joint"],
                     fo[0].data_ptr(), fo[1].data_ptr(), fo[2].data_ptr(), fo[3].data_ptr(),
                     fo[4].data_ptr() if alph else None, fo[5].data_ptr() if alph else None, fo[6].data_ptr(),
                     st.data_ptr()))
@@ -426,7 +436,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"], "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)",
-                   "sharding": (f"scales over {world} ranks + all-to-all to row shards" if strong else
+                   "sharding": ((f"scales over {world} ranks, epilogue stores into peer row shards over NVLink (CUDA IPC)"
+                                 if p2p else f"scales over {world} ranks + NCCL all-to-all to row shards") if strong else
                                 (f"{world} independent grid pairs, one per rank" if world > 1 else "single GPU"))},
         "clocks": clocks.summary(),
         "e2e": e2e, "gpu_launches": int(launches),

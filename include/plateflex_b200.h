@@ -39,6 +39,7 @@ extern "C" {
 #endif
 
 #define PFX_NA 11 /* azimuths of the fan wavelet, cpwt.f90:37 */
+#define PFX_MAX_SHARDS 16 /* row shards (GPUs) a sharded epilogue can address */
 
 enum pfx_status {
     PFX_OK = 0,
@@ -138,6 +139,28 @@ int pfx_wlet_admit_coh_host(pfx_plan *plan, const double *topo, const double *gr
                             double *ewl_admit, double *wl_coh, double *ewl_coh);
 int pfx_wlet_admit_coh_dev(pfx_plan *plan, const double *topo_dev, const double *grav_dev, int is0, int is1,
                            double *wl_admit_dev, double *ewl_admit_dev, double *wl_coh_dev, double *ewl_coh_dev);
+
+/* ---- multi-GPU: admittance / coherence written straight into row shards ---- */
+/* The scale-sharded CWT of one GPU feeding the row-sharded fit of all GPUs without a
+ * separate exchange step: the epilogue kernel of every scale in [is0, is1) stores its four output rows
+ * directly into the buffer of the shard that owns each grid row -- shard q owns rows
+ * [q*R, min((q+1)*R, ny)), R = ceil(ny / nshards) -- at the position pfx_l2_fit_rows_dev expects:
+ *     shard_bases[q][ ((map*ns + scale)*rows_q + (row - q*R))*nx + x ],  map = admit, eadmit, coh, ecoh.
+ * shard_bases[q] is a device pointer valid on this GPU: local memory for the own shard, memory of a peer
+ * GPU mapped with pfx_ipc_open for the others (plain stores over NVLink; the transfer overlaps the
+ * transform scale by scale).  Every rank must synchronise its stream and meet the others at a barrier
+ * before any shard is read. */
+int pfx_wlet_admit_coh_sharded_dev(pfx_plan *plan, const double *topo_dev, const double *grav_dev, int is0, int is1,
+                                   int nshards, void *const *shard_bases);
+/* bytes of shard q's buffer: 4 * ns * rows_q * nx * sizeof(double) */
+size_t pfx_shard_bytes(int nx, int ny, int ns, int nshards, int q);
+/* Device memory that other processes on the node can map (cudaMalloc + cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle).  handle is PFX_IPC_HANDLE_BYTES opaque bytes to be passed between processes. */
+#define PFX_IPC_HANDLE_BYTES 64
+int pfx_ipc_alloc(int device, size_t bytes, void **dev_ptr, unsigned char *handle);
+int pfx_ipc_free(int device, void *dev_ptr);
+int pfx_ipc_open(int device, const unsigned char *handle, void **peer_ptr);
+int pfx_ipc_close(int device, void *peer_ptr);
 
 /* ---- cube-input forms: the literal f2py signatures --------------------- */
 /* For callers that already hold wl_trans cubes (classes.py:277, 966).  Host

@@ -65,6 +65,12 @@ _SIGS = {
     "pfx_wlet_xscalogram_dev": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "pfx_wlet_admit_coh_host": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_wlet_admit_coh_dev": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "pfx_wlet_admit_coh_sharded_dev": ([_vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "pfx_shard_bytes": ([_i, _i, _i, _i, _i], C.c_size_t),
+    "pfx_ipc_alloc": ([_i, C.c_size_t, C.POINTER(_vp), _vp], _i),
+    "pfx_ipc_free": ([_i, _vp], _i),
+    "pfx_ipc_open": ([_i, _vp, C.POINTER(_vp)], _i),
+    "pfx_ipc_close": ([_i, _vp], _i),
     "pfx_cube_scalogram_host": ([_i, _i, _i, _i, _vp, _vp, _vp], _i),
     "pfx_cube_xscalogram_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_cube_admit_coh_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),

@@ -337,7 +337,7 @@ int check_range(const pfx_plan *pl, int is0, int is1)
 // h_outs (optional): host destinations of the outputs; each finished scale is copied back on the copy
 // stream while later scales are still being computed.  elems[i] = doubles per cell of output i.
 int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *d_outs,
-            double *const *h_outs, const int *elems, int nouts)
+            double *const *h_outs, const int *elems, int nouts, const ShardOut *shards = nullptr)
 {
     const int ngrids = g2 ? 2 : 1;
     const size_t nxy = (size_t)pl->nx * pl->ny;
@@ -376,9 +376,14 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
             PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, red_stream));
         } else {
             double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-            for (int i = 0; i < nouts; i++) o[i] = d_outs[i] + so * elems[i];
+            for (int i = 0; i < nouts && d_outs; i++) o[i] = d_outs[i] + so * elems[i];
             ProfScope prof(pl, PFX_KC_REDUCE, red_stream);
-            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream));
+            ShardOut sh;
+            if (shards) {
+                sh = *shards;
+                sh.scale = is;
+            }
+            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream, shards ? &sh : nullptr));
         }
         pl->launches++;
         if (overlap || h_outs) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));
@@ -530,6 +535,80 @@ int pfx_wlet_admit_coh_host(pfx_plan *pl, const double *topo, const double *grav
     double *outs[4] = {wl_admit, ewl_admit, wl_coh, ewl_coh};
     const int el[4] = {1, 1, 1, 1};
     return run_cwt_host(pl, RED_ADMIT_COH, topo, grav, is0, is1, outs, el, 4);
+}
+
+// ---- row-sharded epilogue and IPC-mappable buffers ---------------------------------------
+int pfx_wlet_admit_coh_sharded_dev(pfx_plan *pl, const double *topo, const double *grav, int is0, int is1, int nshards,
+                                   void *const *shard_bases)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(topo && grav && shard_bases, "null pointer");
+    PFX_ARG(nshards >= 1 && nshards <= PFX_MAX_SHARDS, "nshards must be in [1, PFX_MAX_SHARDS]");
+    ShardOut sh;
+    sh.nshards = nshards;
+    sh.rows_per_shard = (pl->ny + nshards - 1) / nshards;
+    sh.ns = pl->ns;
+    for (int q = 0; q < nshards; q++) {
+        const bool has_rows = q * sh.rows_per_shard < pl->ny;
+        PFX_ARG(shard_bases[q] || !has_rows, "null shard buffer");
+        sh.base[q] = reinterpret_cast<double *>(shard_bases[q]);
+    }
+    DeviceGuard guard(pl->device);
+    const int el[4] = {1, 1, 1, 1};
+    return run_cwt(pl, RED_ADMIT_COH, topo, grav, is0, is1, nullptr, nullptr, el, 4, &sh);
+}
+
+size_t pfx_shard_bytes(int nx, int ny, int ns, int nshards, int q)
+{
+    if (nx < 1 || ny < 1 || ns < 1 || nshards < 1 || q < 0 || q >= nshards) return 0;
+    const int R = (ny + nshards - 1) / nshards;
+    const int lo = q * R < ny ? q * R : ny, hi = (q + 1) * R < ny ? (q + 1) * R : ny;
+    return (size_t)4 * ns * (hi - lo) * nx * sizeof(double);
+}
+
+int pfx_ipc_alloc(int device, size_t bytes, void **dev_ptr, unsigned char *handle)
+{
+    PFX_ARG(dev_ptr && handle, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= PFX_IPC_HANDLE_BYTES, "IPC handle does not fit");
+    DeviceGuard guard(device);
+    *dev_ptr = nullptr;
+    PFX_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 16));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return PFX_ERR_CUDA;
+    }
+    memset(handle, 0, PFX_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return PFX_OK;
+}
+
+int pfx_ipc_free(int device, void *dev_ptr)
+{
+    DeviceGuard guard(device);
+    if (dev_ptr) PFX_CUDA(cudaFree(dev_ptr));
+    return PFX_OK;
+}
+
+int pfx_ipc_open(int device, const unsigned char *handle, void **peer_ptr)
+{
+    PFX_ARG(handle && peer_ptr, "null pointer");
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    *peer_ptr = nullptr;
+    PFX_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PFX_OK;
+}
+
+int pfx_ipc_close(int device, void *peer_ptr)
+{
+    DeviceGuard guard(device);
+    if (peer_ptr) PFX_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return PFX_OK;
 }
 
 // ---- cube-input forms -----------------------------------------------------------------

@@ -64,13 +64,25 @@ struct PlaneView {
 
 enum ReduceMode { RED_SCALOGRAM = 0, RED_XSCALOGRAM = 1, RED_ADMIT_COH = 2 };
 
+// Row-sharded destination of the admittance / coherence epilogue (multi-GPU): grid row j
+// belongs to shard q = j / rows_per_shard, whose buffer -- possibly the memory of a peer GPU mapped through
+// CUDA IPC, written with plain stores over NVLink -- holds four maps laid out [map][scale][row in shard][x]
+// for all ns scales, i.e. exactly the (nx, rows, ns) input of pfx_l2_fit_rows_dev on that GPU.
+struct ShardOut {
+    int nshards = 0;  // 0: not sharded
+    int rows_per_shard = 0;
+    int ns = 0;      // scales of the whole transform (slab stride of the destination maps)
+    int scale = 0;   // global index of the scale being reduced
+    double *base[PFX_MAX_SHARDS] = {};
+};
+
 // K3: azimuth reduction + running-prefix jackknife for one scale.
 //   RED_SCALOGRAM : w1 -> out0 = wl_sg, out1 = ewl_sg                       (cpwt.f90:200-241)
 //   RED_XSCALOGRAM: w1,w2 -> out0 = wl_xsg (complex), out1 = ewl_xsg        (cpwt.f90:250-293)
 //   RED_ADMIT_COH : w1,w2 -> out0..3 = wl_admit, ewl_admit, wl_coh, ewl_coh (cpwt.f90:303-364)
 // Each out* points at the (nx, ny) plane of this scale (x fastest).
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream);
+                  double *out3, cudaStream_t stream, const ShardOut *shards = nullptr);
 
 // K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab.
 int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream);

@@ -788,7 +788,6 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
         }
 
         // residuals r = (model - y)/sigma; accumulate cost, J^T r, J^T J over the group's scales
-        const double cdeep = 2. * FLEX_PI * FLEX_GC * fc.drho, ctop = 2. * FLEX_PI * FLEX_GC * (fc.A * fc.rcf);
         auto evaluate = [&](const double(&x)[NP], Normal<NP> &nm) {
             const double te = x[0], F = x[1];
             const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292

@@ -130,15 +130,26 @@ __device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int 
     return make_double2(w.x * v.scale, w.y * v.scale);
 }
 
-template <int MODE>
+template <int MODE, bool SHARDED>
 __global__ void __launch_bounds__(128, 4)
     reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
-                  double *__restrict__ out2, double *__restrict__ out3)
+                  double *__restrict__ out2, double *__restrict__ out3, ShardOut sh)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= nx) return;
-    const size_t o = (size_t)j * nx + i;
+    size_t o = (size_t)j * nx + i;
+    if (SHARDED) {
+        // the four maps of the shard that owns row j: [map][scale][row in shard][x]
+        const int q = j / sh.rows_per_shard, jl = j - q * sh.rows_per_shard;
+        const int rq = min(sh.rows_per_shard, ny - q * sh.rows_per_shard);
+        const size_t map_stride = (size_t)sh.ns * rq * nx;
+        out0 = sh.base[q];
+        out1 = out0 + map_stride;
+        out2 = out1 + map_stride;
+        out3 = out2 + map_stride;
+        o = ((size_t)sh.scale * rq + jl) * nx + i;
+    }
     const double2 z1 = load_z(w1, i, j);
     const double2 z2 = (MODE == RED_SCALOGRAM) ? z1 : load_z(w2, i, j);
 
@@ -204,18 +215,26 @@ __global__ void crop_kernel(int nx, int ny, PlaneView w, double2 *__restrict__ s
 }  // namespace
 
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream)
+                  double *out3, cudaStream_t stream, const ShardOut *shards)
 {
     dim3 block(128), grid((nx + 127) / 128, ny);
+    const ShardOut none;
+    if (shards && shards->nshards > 0) {
+        PFX_ARG(mode == RED_ADMIT_COH, "row-sharded output exists for the admittance / coherence epilogue only");
+        reduce_kernel<RED_ADMIT_COH, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr, nullptr,
+                                                                    *shards);
+        PFX_CUDA(cudaGetLastError());
+        return PFX_OK;
+    }
     switch (mode) {
         case RED_SCALOGRAM:
-            reduce_kernel<RED_SCALOGRAM><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            reduce_kernel<RED_SCALOGRAM, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         case RED_XSCALOGRAM:
-            reduce_kernel<RED_XSCALOGRAM><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            reduce_kernel<RED_XSCALOGRAM, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         case RED_ADMIT_COH:
-            reduce_kernel<RED_ADMIT_COH><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3);
+            reduce_kernel<RED_ADMIT_COH, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         default:
             set_error("launch_reduce: bad mode %d", mode);

@@ -16,7 +16,7 @@ CPU tensors with the gloo backend (tests/test_sharding.py) and on CUDA tensors w
 import torch
 import torch.distributed as dist
 
-__all__ = ["scale_range", "balanced_cuts", "row_range", "rows_per_shard", "RowResharder", "gather_rows"]
+__all__ = ["scale_range", "balanced_cuts", "row_range", "rows_per_shard", "RowResharder", "PeerShards", "gather_rows"]
 
 
 def scale_range(ns, world, rank, cost=None):
@@ -124,6 +124,60 @@ class RowResharder:
     def local_maps(self):
         """Flat tensors of this rank's (nx, nrows, ns) maps (all scales, rows [row0, row0+nrows))."""
         return self.recv
+
+
+class PeerShards:
+    """One-sided form of the exchange: every rank owns an IPC-mappable buffer holding its row shard
+    of the four maps for all scales ([map][scale][row][x]); the other ranks map it (CUDA IPC) and
+    the admittance / coherence epilogue of ``pfx_wlet_admit_coh_sharded_dev`` stores each output
+    row straight into the owner's buffer over NVLink while the transform of the next scale runs.
+    No pack kernel, no collective on the data path -- only a barrier before the fit reads."""
+
+    def __init__(self, nx, ny, ns, world, rank, device_index, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.nx, self.ny, self.ns, self.world, self.rank, self.group = nx, ny, ns, world, rank, group
+        self.device = device_index
+        self.row0, row1 = row_range(ny, world, rank)
+        self.nrows = row1 - self.row0
+        nbytes = _lib.lib.pfx_shard_bytes(nx, ny, ns, world, rank)
+        self.own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _lib.check(_lib.lib.pfx_ipc_alloc(device_index, max(nbytes, 16), C.byref(self.own), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.bases = (C.c_void_p * world)()
+        self._opened = []
+        for q in range(world):
+            if q == rank:
+                self.bases[q] = self.own.value
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+            _lib.check(_lib.lib.pfx_ipc_open(device_index, buf, C.byref(p)))
+            self.bases[q] = p.value
+            self._opened.append(p)
+
+    def transform(self, plan, topo_ptr, grav_ptr, is0, is1):
+        """Enqueue the CWT of scales [is0, is1) with the sharded epilogue on the plan's stream."""
+        if is1 > is0:
+            self._lib.check(self._lib.lib.pfx_wlet_admit_coh_sharded_dev(plan.handle, topo_ptr, grav_ptr, is0, is1,
+                                                                         self.world, self.bases))
+
+    def local_map_ptrs(self):
+        """Device pointers of this rank's four (nx, nrows, ns) maps."""
+        stride = self.ns * self.nrows * self.nx * 8
+        return [self.own.value + m * stride for m in range(4)]
+
+    def close(self):
+        for p in self._opened:
+            self._lib.lib.pfx_ipc_close(self.device, p)
+        self._opened = []
+        if self.own:
+            self._lib.lib.pfx_ipc_free(self.device, self.own)
+            self.own = None
 
 
 def gather_rows(local, nx_out, out_rows, group=None):

@@ -366,3 +366,85 @@ def test_row_sharded_fit_equals_full_grid_fit(pf, nn, world, alph):
         assert got.shape == full[n].shape, (n, got.shape, full[n].shape)
         assert np.array_equal(got, full[n], equal_nan=True), n
     assert (full["status"] == 1).sum() > 0
+
+
+@pytest.mark.parametrize("with_grids", [False, True])
+def test_ocean_free_air_project_with_alpha_matches_scipy(pf, ora, with_grids):
+    """BASELINE configs[3] in small: free-air gravity over ocean (wd > 0 per cell, water-loaded model),
+    3-parameter fit (alpha), optionally per-cell crustal density / thickness grids (classes.py:1087-1091),
+    against SciPy TRF on the oracle model with each cell's own constants."""
+    from oracle import l2fit
+    from plateflex_b200 import _lib, synthetic
+    pf.set_conf_cpwt()
+    pf.set_conf_flex()
+    _lib.clear_plans()
+    nx, ny, dx, dy = 40, 36, 20.0, 20.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240004, Te=20.0, F=0.2, boug=False, ocean_depth=4000.0,
+                                     rhoc=2800.0)
+    grids = [pf.TopoGrid(topo.copy(), dx, dy), pf.FairGrid(grav, dx, dy)]
+    rhoc = zc = None
+    if with_grids:
+        rhoc = 2800.0 + 60.0 * red_field(nx, ny, seed=5)
+        zc = 30.0e3 + 3.0e3 * red_field(nx, ny, seed=6)
+        grids += [pf.RhocGrid(rhoc.copy(), dx, dy), pf.ZcGrid(zc.copy(), dx, dy)]
+    else:
+        pf.cf_fl.rhoc = 2800.0
+    proj = pf.Project(grids=grids)
+    proj.init()
+    assert pf.cf_fl.boug == 0 and (proj.water_depth > 0).all()
+    proj.wlet_admit_coh()
+    nn = 7
+    proj.estimate_grid(nn=nn, alph=True, atype="joint")
+    maps = (proj.wl_admit, proj.ewl_admit, proj.wl_coh, proj.ewl_coh)
+    checked = 0
+    for ci, i in enumerate(range(0, nx - nn, nn)):
+        for cj, j in enumerate(range(0, ny - nn, nn)):
+            conf = ora.FlexConf(wd=float(proj.water_depth[i, j]), boug=0,
+                                rhoc=float(rhoc[i, j]) if with_grids else 2800.0,
+                                zc=float(zc[i, j]) if with_grids else 35.0e3)
+            r = l2fit.L2_estimate_cell(proj.k, *[m[i, j] for m in maps], alph=True, atype="joint", conf=conf)
+            gm = [proj.mean_Te_grid[ci, cj], proj.mean_F_grid[ci, cj], proj.mean_a_grid[ci, cj]]
+            gs = [proj.std_Te_grid[ci, cj], proj.std_F_grid[ci, cj], proj.std_a_grid[ci, cj]]
+            assert proj.status_grid[ci, cj] == 1
+            checked += _compare_fit(gm, gs, proj.chi2_grid[ci, cj], r["mean"], r["std"], r["chi2"], 3)
+    assert checked >= 5
+    pf.set_conf_flex()
+
+
+@pytest.mark.parametrize("nshards", [1, 3, 8])
+def test_sharded_epilogue_writes_the_row_shard_layout(pf, engine, nshards):
+    """pfx_wlet_admit_coh_sharded_dev (the multi-GPU epilogue that stores into the owners' row shards; here all
+    shards are local buffers) must reproduce the plain outputs bit for bit in the [map][scale][row][x] layout
+    that pfx_l2_fit_rows_dev reads, for scale blocks enqueued separately as different ranks would."""
+    import ctypes as C
+    import torch
+    from plateflex_b200 import _lib, classes, sharding, synthetic
+    from plateflex_b200.cpwt import fused
+    nx, ny, dx, dy = 37, 29, 20.0, 20.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240021, Te=30.0, F=0.4)
+    k = classes._lam2k(nx, ny, dx, dy)[1][:7]
+    ns = len(k)
+    want = fused.wlet_admit_coh(topo, grav, dx, dy, k)  # (nx, ny, ns) Fortran-ordered
+    dev = torch.device("cuda", _lib.default_device())
+    plan = _lib.get_plan(nx, ny, dx, dy, k, pf.cf_wt.k0)
+    d_t, d_g = torch.from_numpy(topo).to(dev), torch.from_numpy(grav).to(dev)
+    bufs = []
+    for q in range(nshards):
+        nbytes = _lib.lib.pfx_shard_bytes(nx, ny, ns, nshards, q)
+        r0, r1 = sharding.row_range(ny, nshards, q)
+        assert nbytes == 4 * ns * (r1 - r0) * nx * 8
+        bufs.append(torch.full((max(nbytes // 8, 1),), np.nan, dtype=torch.float64, device=dev))
+    bases = (C.c_void_p * nshards)(*[b.data_ptr() for b in bufs])
+    for r in range(2):  # two "ranks", each with its block of scales
+        is0, is1 = sharding.scale_range(ns, 2, r)
+        _lib.check(_lib.lib.pfx_wlet_admit_coh_sharded_dev(plan.handle, d_t.data_ptr(), d_g.data_ptr(), is0, is1,
+                                                           nshards, bases))
+    torch.cuda.synchronize()
+    for q in range(nshards):
+        r0, r1 = sharding.row_range(ny, nshards, q)
+        if r1 == r0:
+            continue
+        got = bufs[q].cpu().numpy()[:4 * ns * (r1 - r0) * nx].reshape(4, ns, r1 - r0, nx)
+        for m in range(4):
+            ref = np.transpose(want[m], (2, 1, 0))[:, r0:r1, :]
+            assert np.array_equal(got[m], ref, equal_nan=True), (q, m)
