@@ -1,5 +1,6 @@
 // pfx_api.cu -- C ABI of libplateflex_b200.so: plan management and the CWT entry
 // points declared in include/plateflex_b200.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -139,6 +140,7 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
     pl->dy = dy_km;
     pl->k0 = k0;
     pl->engine = engine;
+    pl->spec_t = engine == PFX_ENGINE_PRUNED;
     pl->device = device;
     pl->k.assign(k_rad_m, k_rad_m + ns);
 
@@ -195,7 +197,8 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
             pl->fft_fwd_ok = true;
             r = cufftSetAutoAllocation(pl->fft_fwd, 0);
         }
-        int n[2] = {pl->NY, pl->NX};
+        int n[2] = {pl->NY, pl->NX};  // slowest first
+        if (pl->spec_t) std::swap(n[0], n[1]);
         if (r == CUFFT_SUCCESS) r = cufftMakePlanMany(pl->fft_fwd, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2Z, 1, &ws);
         if (r != CUFFT_SUCCESS) {
             set_error("cufft forward plan %dx%d failed: %d", pl->NY, pl->NX, (int)r);

@@ -75,6 +75,22 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Same for the y-fastest device layout of the pruned engine (element (i, j) at [i*NY + j], spectrum
+// (a, b) at [a*NY + b]): input and output share the fast axis, no transposition.
+__global__ void __launch_bounds__(256)
+    mirror_pad_t_kernel(const double *__restrict__ grid, int nx, int ny, int NY, const double *__restrict__ mean_ptr,
+                        double2 *__restrict__ xpad)
+{
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x, ii = blockIdx.y;
+    if (jj >= ny) return;
+    const double2 v = make_double2(grid[(size_t)ii * ny + jj] - *mean_ptr, 0.0);
+    const int im = 2 * nx - 1 - ii, jm = 2 * ny - 1 - jj;
+    xpad[(size_t)ii * NY + jj] = v;
+    xpad[(size_t)ii * NY + jm] = v;
+    xpad[(size_t)im * NY + jj] = v;
+    xpad[(size_t)im * NY + jm] = v;
+}
+
 // ---- wavenumber axes and the scale-independent admissibility factors --------------
 // defk (cpwt_sub.f90:41-62): index a <= n/2 -> +a*dk (Nyquist positive), else (a-n)*dk.
 __global__ void axes_kernel(int n, double d_km, double *__restrict__ kk, double *__restrict__ g2)
@@ -144,8 +160,13 @@ int forward_spectrum(pfx_plan *pl, const double *grid_dev, int slot)
         PFX_CUDA(cudaMemsetAsync(xp, 0, P * sizeof(double2), pl->stream));
         pl->launches++;
     }
-    dim3 grid((pl->nx + 31) / 32, (pl->ny + 31) / 32), block(32, 8);
-    mirror_pad_kernel<<<grid, block, 0, pl->stream>>>(grid_dev, pl->nx, pl->ny, pl->NX, pl->d_partial + SUM_BLOCKS, xp);
+    if (pl->spec_t) {
+        mirror_pad_t_kernel<<<dim3((pl->ny + 255) / 256, pl->nx), 256, 0, pl->stream>>>(
+            grid_dev, pl->nx, pl->ny, pl->NY, pl->d_partial + SUM_BLOCKS, xp);
+    } else {
+        dim3 grid((pl->nx + 31) / 32, (pl->ny + 31) / 32), block(32, 8);
+        mirror_pad_kernel<<<grid, block, 0, pl->stream>>>(grid_dev, pl->nx, pl->ny, pl->NX, pl->d_partial + SUM_BLOCKS, xp);
+    }
     PFX_CUDA(cudaGetLastError());
     PFX_CUFFT(cufftSetStream(pl->fft_fwd, pl->stream));
     PFX_CUFFT(cufftExecZ2Z(pl->fft_fwd, (cufftDoubleComplex *)xp, (cufftDoubleComplex *)xp, CUFFT_FORWARD));

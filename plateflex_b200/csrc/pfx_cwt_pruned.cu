@@ -74,13 +74,13 @@ __global__ void twiddle_kernel(int logN, int logL, const int *lo, const double2 
     tw[((size_t)ia << logN) + e] = root[idx];
 }
 
-// Admissibility term: plane[g][b][a] = exp(-kx^2/2) exp(-ky^2/2) X_g[b][a]   (cpwt_sub.f90:93)
+// Admissibility term on the y-fastest layout: plane[g][a][b] = exp(-kx^2/2) exp(-ky^2/2) X_g[a][b]   (cpwt_sub.f90:93)
 __global__ void zmul_kernel(int NX, int NY, const double2 *__restrict__ s0, const double2 *__restrict__ s1,
                             const double *__restrict__ u2, const double *__restrict__ v2, double2 *planes)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (a >= NX) return;
-    const size_t o = (size_t)b * NX + a, P = (size_t)NX * NY;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= NY) return;
+    const size_t o = (size_t)a * NY + b, P = (size_t)NX * NY;
     const double w = u2[a] * v2[b];
     const double2 x0 = s0[o];
     planes[o] = make_double2(w * x0.x, w * x0.y);
@@ -90,13 +90,25 @@ __global__ void zmul_kernel(int NX, int NY, const double2 *__restrict__ s0, cons
     }
 }
 
-__global__ void zcrop_kernel(int nx, int ny, int NX, size_t P, double scale, const double2 *__restrict__ planes,
-                             double2 *zc)
+// zc[g][j][i] = scale * plane[g][i+1][j+1]: crop with the one-sample shift, transposed to the x-fastest
+// layout of the coefficient planes through a 32 x 32 shared-memory tile
+__global__ void __launch_bounds__(256)
+    zcrop_kernel(int nx, int ny, int NY, size_t P, double scale, const double2 *__restrict__ planes, double2 *zc)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, g = blockIdx.z;
-    if (i >= nx) return;
-    const double2 v = planes[g * P + (size_t)(j + 1) * NX + (i + 1)];
-    zc[((size_t)g * ny + j) * nx + i] = make_double2(v.x * scale, v.y * scale);
+    __shared__ double2 tile[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32, g = blockIdx.z;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + threadIdx.x;
+        if (i < nx && j < ny) tile[r][threadIdx.x] = planes[g * P + (size_t)(i + 1) * NY + (j + 1)];
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += 8) {
+        const int i = i0 + threadIdx.x, j = j0 + c;
+        if (i < nx && j < ny) {
+            const double2 v = tile[threadIdx.x][c];
+            zc[((size_t)g * ny + j) * nx + i] = make_double2(v.x * scale, v.y * scale);
+        }
+    }
 }
 
 int ilog2(int v)
@@ -320,8 +332,8 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CUDA(cudaGetLastError());
     PFX_CUDA(cudaStreamSynchronize(pl->stream));  // h_lo / h_k0 go out of scope
 
-    // dense inverse plans for the admissibility term (1 or 2 planes)
-    int n[2] = {NY, NX};
+    // dense inverse plans for the admissibility term (1 or 2 planes), y-fastest layout
+    int n[2] = {NX, NY};
     size_t need = pl->fft_work_bytes;
     for (int g = 0; g < 2; g++) {
         size_t ws = 0;
@@ -380,14 +392,14 @@ int pruned_prepare(pfx_plan *pl, int ngrids)
     PrunedState *st = state_of(pl);
     const size_t P = (size_t)pl->NX * pl->NY;
     ProfScope prof(pl, PFX_KC_PREPARE, pl->stream);
-    zmul_kernel<<<dim3((pl->NX + 255) / 256, pl->NY), 256, 0, pl->stream>>>(
+    zmul_kernel<<<dim3((pl->NY + 255) / 256, pl->NX), 256, 0, pl->stream>>>(
         pl->NX, pl->NY, pl->d_spec[0], ngrids == 2 ? pl->d_spec[1] : nullptr, pl->d_u2, pl->d_v2, st->zplanes);
     PFX_CUDA(cudaGetLastError());
     cufftHandle h = st->fft_z[ngrids - 1];
     PFX_CUFFT(cufftSetStream(h, pl->stream));
     PFX_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *)st->zplanes, (cufftDoubleComplex *)st->zplanes, CUFFT_INVERSE));
-    zcrop_kernel<<<dim3((pl->nx + 127) / 128, pl->ny, ngrids), 128, 0, pl->stream>>>(pl->nx, pl->ny, pl->NX, P,
-                                                                                     1.0 / (double)P, st->zplanes, st->zc);
+    zcrop_kernel<<<dim3((pl->nx + 31) / 32, (pl->ny + 31) / 32, ngrids), dim3(32, 8), 0, pl->stream>>>(
+        pl->nx, pl->ny, pl->NY, P, 1.0 / (double)P, st->zplanes, st->zc);
     PFX_CUDA(cudaGetLastError());
     pl->launches += 3;
     return PFX_OK;

@@ -44,8 +44,11 @@ struct pfx_plan {
     // wavenumber axes (defk, cpwt_sub.f90:41-62) and the scale-independent
     // admissibility factors exp(-kx^2/2), exp(-ky^2/2) (cpwt_sub.f90:93)
     double *d_kx = nullptr, *d_ky = nullptr, *d_u2 = nullptr, *d_v2 = nullptr;
-    // padded spectra of up to two grids, layout [b][a] (a = x-wavenumber fastest)
+    // padded spectra of up to two grids: layout [b][a] (a = x-wavenumber fastest) for the dense engine,
+    // [a][b] (spec_t: y-wavenumber fastest, so that pass 1 of the pruned engine reads its columns
+    // contiguously) for the pruned engine -- the 2-D transform of the transposed grid
     double2 *d_spec[2] = {nullptr, nullptr};
+    bool spec_t = false;
     double *d_partial = nullptr;  // deterministic two-stage sum for the mean
     cufftHandle fft_fwd = 0;
     bool fft_fwd_ok = false;

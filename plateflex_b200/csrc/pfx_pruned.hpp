@@ -61,7 +61,7 @@ struct ScaleDesc {
 struct PrunedArgs {
     ScaleDesc sd;
     int nx, ny, NX, NY, ngrids;
-    const double2 *spec0, *spec1;  // padded spectra [b][a]
+    const double2 *spec0, *spec1;  // padded spectra [a][b] (y-wavenumber fastest)
     const double *tabu, *tabv;     // weight tables (all scales)
     const double2 *twa, *twb;      // stage-1 twiddle tables (all scales)
     const double2 *rootx, *rooty;  // exp(2 pi i m / N)

@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(NT, 3) pass1_kernel(PrunedArgs a)
     const double2 *spec = g ? a.spec1 : a.spec0;
     const double *tv = a.tabv + sd.tabv + ((size_t)ia << LOGL);
     const double2 *tw = a.twb + sd.twb + ((size_t)ia << A.logN);
-    const int NXl = a.NX, NYm = a.NY - 1;
+    const int NYl = a.NY, NYm = a.NY - 1;
     const bool staged = A.r > 1;
     for (int m = blockIdx.x; m < sd.ka[ia]; m += gridDim.x) {
-        const double2 *scol = spec + ((sd.alo[ia] + m) & (a.NX - 1));
+        const double2 *scol = spec + (size_t)((sd.alo[ia] + m) & (a.NX - 1)) * NYl;  // spectrum is [a][b]
         auto from_global = [&](int, int mb) {
-            const double2 x = __ldg(scol + (size_t)((lo + mb) & NYm) * NXl);
+            const double2 x = __ldg(scol + ((lo + mb) & NYm));
             const double wv = tv[mb];
             return make_double2(x.x * wv, x.y * wv);
         };

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(NT, (CPC == 1 && !PREFETCH && !MULTI) ? 3 : 2)
 // ---- pass 1: y-direction transforms, CPC consecutive spectrum columns per group ---------------------------
 template <int CPC>
 struct Pass1Group {
-    const double2 *spec;  // padded spectrum [b][a]
+    const double2 *spec;  // padded spectrum [a][b] (y-wavenumber fastest)
     const double *tv;     // v1 weights of this azimuth [L]
     const double *tu;     // (c/P) u1 weights of this azimuth [Lx]
     double2 *Tt;          // T[t][m][j]
@@ -267,7 +267,7 @@ struct Pass1Group {
     {
         const int m = g * CPC + c;
         if (CPC > 1 && m >= ka) return make_double2(0., 0.);
-        const double2 x = __ldg(spec + (size_t)((blo + mb) & NYm) * NX + ((alo + m) & (NX - 1)));
+        const double2 x = __ldg(spec + (size_t)((alo + m) & (NX - 1)) * (NYm + 1) + ((blo + mb) & NYm));
         const double wv = tv[mb];
         return make_double2(x.x * wv, x.y * wv);
     }

@@ -17,17 +17,15 @@ namespace {
 constexpr int NA = PFX_NA;
 
 // 1/x to ~1 ulp without the special-case branches of the IEEE division sequence: the hardware
-// seed (rcp.approx.ftz.f64, >= 20 bits) and two Newton steps.  x == 0 or non-finite yields inf / NaN,
-// which the callers replace by the reference's guarded values.
+// seed (rcp.approx.ftz.f64, >= 20 bits) and one third-order step r(1 + e + e^2), e = 1 - x r, whose
+// error is e^3 < 2^-60.  x == 0 or non-finite yields inf / NaN, which the callers replace by the
+// reference's guarded values.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 
 __device__ __forceinline__ double jk_spread(const double (&v2)[NA])
@@ -76,8 +74,11 @@ __device__ __forceinline__ void ratio(double q1, double q2, double qx, double &a
     // One branch-free reciprocal serves both quotients (ad = xp*p2/(p1*p2)), and the divisions by the
     // constants na, na-1 are multiplications: the results differ from the reference's IEEE divisions by
     // a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
-    const double xr = qx * fast_rcp(q1 * q2);
-    const bool ok = (q1 != 0.0) & (q2 != 0.0);
+    // The sums are non-negative, so "a sum is 0" is "the product is 0"; the test reads the exponent and
+    // mantissa bits with integer instructions and leaves the FP64 pipe to the arithmetic.
+    const double prod = q1 * q2;
+    const double xr = qx * fast_rcp(prod);
+    const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
     co = ok ? qx * xr : 0.0;
     ad = ok ? q2 * xr : 0.0;
 }

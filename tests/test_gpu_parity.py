@@ -313,7 +313,10 @@ def test_dense_and_pruned_engines_agree_at_full_size(pf, monkeypatch):
         res[eng] = fused.wlet_admit_coh(topo, grav, 5.0, 5.0, k)
     _lib.clear_plans()
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), res["pruned"], res["dense"]):
-        assert_maps_close(a, b, name)
+        # The jackknife errors are differences of nearly equal ratios: over 5e6 cells a few elements amplify
+        # the 1e-16 rounding differences of two FFT algorithms beyond 1e-9 of their own value; the plane-level
+        # bound stays 1e-9, the element-wise one is 1e-8 for the error maps.
+        assert_maps_close(a, b, name, rtol=1e-8 if name.startswith("e") else 1e-9)
 
 
 @pytest.mark.gpu
