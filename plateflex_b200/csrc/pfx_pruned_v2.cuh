@@ -69,8 +69,74 @@ __device__ __forceinline__ void load_stage_twiddles(double2 *stw, int logN, cons
     }
 }
 
+// a <- a + w b, b <- a - w b in six fused multiply-adds (the difference as 2a - (a + w b)).
+__device__ __forceinline__ void bfly(double2 &a, double2 &b, const double2 w)
+{
+    const double pr = fma(w.x, b.x, fma(-w.y, b.y, a.x));
+    const double pi = fma(w.x, b.y, fma(w.y, b.x, a.y));
+    b = make_double2(fma(2.0, a.x, -pr), fma(2.0, a.y, -pi));
+    a = make_double2(pr, pi);
+}
+// a <- a + w b only (four fused multiply-adds): the last stage of a line whose upper half is never stored
+__device__ __forceinline__ void bfly_plus(double2 &a, const double2 b, const double2 w)
+{
+    a = make_double2(fma(w.x, b.x, fma(-w.y, b.y, a.x)), fma(w.x, b.y, fma(w.y, b.x, a.y)));
+}
+__device__ __forceinline__ double2 csqr(const double2 w) { return make_double2(fma(w.x, w.x, -(w.y * w.y)), 2.0 * (w.x * w.y)); }
+__device__ __forceinline__ double2 times_i(const double2 w) { return make_double2(-w.y, w.x); }
+
+// Twiddled radix-R butterfly, X[k] = sum_j W_R^{jk} w^j v[j] (W_R = exp(+2 pi i / R)), as log2(R) levels of
+// radix-2 butterflies whose twiddles are w^(R/2), ..., w^2, w times the fixed eighth roots: 12 x 6 + 10
+// instructions for R = 8 where "multiply the inputs by w^j, then a plain DFT" takes 108.  Output k is left in
+// v[bitrev(k)]; with HALF only X[0 .. R/2) are computed (v[bitrev(k)] for k >= R/2 is garbage).
+template <int R, bool HALF>
+__device__ __forceinline__ void tw_dft(double2 (&v)[R], const double2 w)
+{
+    if constexpr (R == 8) {
+        constexpr double H = 0.70710678118654752440;
+        const double2 w2 = csqr(w), w4 = csqr(w2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) bfly(v[j], v[j + 4], w4);
+        const double2 iw2 = times_i(w2);
+        bfly(v[0], v[2], w2);
+        bfly(v[1], v[3], w2);
+        bfly(v[4], v[6], iw2);
+        bfly(v[5], v[7], iw2);
+        const double2 w8 = make_double2(H * (w.x - w.y), H * (w.x + w.y));  // w * exp(i pi / 4)
+        if constexpr (HALF) {
+            bfly_plus(v[0], v[1], w);
+            bfly_plus(v[4], v[5], w8);
+            bfly_plus(v[2], v[3], times_i(w));
+            bfly_plus(v[6], v[7], times_i(w8));
+        } else {
+            bfly(v[0], v[1], w);
+            bfly(v[4], v[5], w8);
+            bfly(v[2], v[3], times_i(w));
+            bfly(v[6], v[7], times_i(w8));
+        }
+    } else {
+        static_assert(R == 4, "radix 4 or 8");
+        const double2 w2 = csqr(w);
+        bfly(v[0], v[2], w2);
+        bfly(v[1], v[3], w2);
+        if constexpr (HALF) {
+            bfly_plus(v[0], v[1], w);
+            bfly_plus(v[2], v[3], times_i(w));
+        } else {
+            bfly(v[0], v[1], w);
+            bfly(v[2], v[3], times_i(w));
+        }
+    }
+}
+template <int R>
+__device__ __forceinline__ constexpr int bitrev(int k)
+{
+    return R == 8 ? (((k & 1) << 2) | (k & 2) | ((k >> 2) & 1)) : (((k & 1) << 1) | ((k >> 1) & 1));
+}
+
 // Stage S >= 1 of all CPC lines of a part, in place; the last stage stores through store(c, q, rho, v).
-template <int LOGL, int S, int CPC, class Store>
+// HALF (last stage only): the upper half of the line is never stored (N = 2 nout), so it is not computed.
+template <int LOGL, int S, int CPC, bool HALF, class Store>
 __device__ __forceinline__ void stage(double2 *sm, const double2 *stw_all, const Store &store)
 {
     using G = Geo<LOGL>;
@@ -87,37 +153,39 @@ __device__ __forceinline__ void stage(double2 *sm, const double2 *stw_all, const
         const int u = b >> G::LOGRC;
         const int q0 = u & (M - 1);
         const int base = ((u >> LOGM) << (LOGM + LR)) + q0;
-        double2 tw[R];
-        tw[1] = stw[q0];
-#pragma unroll
-        for (int k = 2; k < R; k++) tw[k] = cmul(tw[k - 1], tw[1]);
+        const double2 w = stw[q0];
 #pragma unroll
         for (int c = 0; c < CPC; c++) {
             double2 *p = sm + c * G::PLANE + rho;
             double2 v[R];
 #pragma unroll
             for (int k = 0; k < R; k++) v[k] = p[padded<G::PAD>(base + k * M) << G::LOGRC];
-#pragma unroll
-            for (int k = 1; k < R; k++) v[k] = cmul(v[k], tw[k]);
-            dft<R>(v);
             if constexpr (LAST) {
+                if (HALF) {
+                    tw_dft<R, true>(v, w);
 #pragma unroll
-                for (int k = 0; k < R; k++) store(c, base + k * M, rho, v[k]);
+                    for (int k = 0; k < R / 2; k++) store(c, base + k * M, rho, v[bitrev<R>(k)]);
+                } else {
+                    tw_dft<R, false>(v, w);
+#pragma unroll
+                    for (int k = 0; k < R; k++) store(c, base + k * M, rho, v[bitrev<R>(k)]);
+                }
             } else {
+                tw_dft<R, false>(v, w);
 #pragma unroll
-                for (int k = 0; k < R; k++) p[padded<G::PAD>(base + k * M) << G::LOGRC] = v[k];
+                for (int k = 0; k < R; k++) p[padded<G::PAD>(base + k * M) << G::LOGRC] = v[bitrev<R>(k)];
             }
         }
     }
 }
 
-template <int LOGL, int S, int CPC, class Store>
+template <int LOGL, int S, int CPC, bool HALF, class Store>
 __device__ __forceinline__ void run_stages(double2 *sm, const double2 *stw, const Store &store)
 {
     if constexpr (S < Geo<LOGL>::NST) {
         __syncthreads();
-        stage<LOGL, S, CPC, Store>(sm, stw, store);
-        run_stages<LOGL, S + 1, CPC, Store>(sm, stw, store);
+        stage<LOGL, S, CPC, HALF, Store>(sm, stw, store);
+        run_stages<LOGL, S + 1, CPC, HALF, Store>(sm, stw, store);
     }
 }
 
@@ -135,6 +203,7 @@ __device__ __forceinline__ void run_lines(double2 *sm, const double2 *stw, const
     constexpr int STEP = G::STEP, L = G::L;
     constexpr bool KEEP = MULTI || PREFETCH;  // support samples persist in registers
     const int Nm = A.N - 1;
+    const bool half = 2 * A.nout == A.N;  // power-of-two grid: outputs q >= L/2 are never stored
     const int l0 = lo & (L - 1), lh = l0 >> G::LOGBF, ll = l0 & (STEP - 1);
 
     // this thread's first-stage butterfly (u, rho): fixed for the whole kernel
@@ -204,7 +273,10 @@ __device__ __forceinline__ void run_lines(double2 *sm, const double2 *stw, const
             }
             const int rho0 = part << G::LOGRC;
             auto store = [&](int c, int q, int rr, double2 v) { grp.store(gi, c, q, rho0 + rr, v); };
-            run_stages<LOGL, 1, CPC>(sm, stw, store);
+            if (half)
+                run_stages<LOGL, 1, CPC, true>(sm, stw, store);
+            else
+                run_stages<LOGL, 1, CPC, false>(sm, stw, store);
             __syncthreads();  // the next first stage overwrites the planes
         }
     }
