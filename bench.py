@@ -338,6 +338,31 @@ def main():
         e2e = {"value": units_job / (e2e_ms * 1e-3), "unit": "units/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": 2 * nxy * 8 * world, "d2h_bytes_per_step": int(per_rank_out.item()),
                "api": "pfx_wlet_admit_coh_host (what Project.wlet_admit_coh calls), pinned host buffers"}
+        # same call with float32 results (the reference's own output dtype; opt-in, set_output_dtype(float32))
+        h_out32 = [torch.empty(max(nsl, 1) * nxy, dtype=torch.float32).pin_memory() for _ in range(4)]
+
+        def step_host32():
+            if nsl > 0:
+                _lib.check(_lib.lib.pfx_wlet_admit_coh_host_f32(plan.handle, h_in[0].data_ptr(), h_in[1].data_ptr(),
+                                                                is0, is1, *[o.data_ptr() for o in h_out32]))
+
+        for _ in range(2):
+            step_host32()
+        barrier()
+        te = []
+        for _ in range(max(3, args.steps // 2)):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            step_host32()
+            te.append((time.perf_counter() - t0) * 1e3)
+        t3 = torch.tensor(te, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        e2e["float32_outputs"] = {"value": units_job / (float(t3.mean().item()) * 1e-3), "unit": "units/s",
+                                  "ms_per_step": float(t3.mean().item()),
+                                  "d2h_bytes_per_step": int(per_rank_out.item()) // 2}
+        del h_out32
 
     # ---- second metric: per-cell L2 fit of the maps (N=1: whole grid; strong: this rank's row shard) ----
     fit = None

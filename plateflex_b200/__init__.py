@@ -15,6 +15,7 @@ from . import estimate
 from .classes import Grid, TopoGrid, GravGrid, BougGrid, FairGrid
 from .classes import RhocGrid, ZcGrid, Project
 from .cpwt import conf_cpwt as cf_wt
+from .cpwt import get_output_dtype, set_output_dtype
 from .flex import conf_flex as cf_fl
 
 

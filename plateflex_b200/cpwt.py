@@ -18,7 +18,24 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["cpwt", "conf_cpwt", "fused"]
+__all__ = ["cpwt", "conf_cpwt", "fused", "set_output_dtype", "get_output_dtype"]
+
+# dtype of the (nx, ny, ns) maps returned by the fused grid-in forms: float64 (default: what the kernels
+# compute) or float32 (what numpy.f2py returns for the reference's REAL arrays; rounded once on the device,
+# half the device-to-host copy)
+_OUT_DTYPE = np.dtype(np.float64)
+
+
+def set_output_dtype(dtype):
+    global _OUT_DTYPE
+    dt = np.dtype(dtype)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("output dtype must be float32 or float64")
+    _OUT_DTYPE = dt
+
+
+def get_output_dtype():
+    return _OUT_DTYPE
 
 
 class _ConfCpwt:
@@ -121,8 +138,9 @@ class _Fused:
         nx, ny = g.shape
         is0, is1 = scales if scales is not None else (0, len(kf))
         plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
-        sg, esg = _maps(nx, ny, is1 - is0, 2)
-        _lib.check(_lib.lib.pfx_wlet_scalogram_host(plan.handle, _lib.ptr(g), is0, is1, _lib.ptr(sg), _lib.ptr(esg)))
+        sg, esg = _maps(nx, ny, is1 - is0, 2, _OUT_DTYPE)
+        fn = _lib.lib.pfx_wlet_scalogram_host_f32 if _OUT_DTYPE == np.float32 else _lib.lib.pfx_wlet_scalogram_host
+        _lib.check(fn(plan.handle, _lib.ptr(g), is0, is1, _lib.ptr(sg), _lib.ptr(esg)))
         return sg, esg
 
     def wlet_xscalogram(self, grid1, grid2, dx, dy, kf, scales=None):
@@ -147,9 +165,12 @@ class _Fused:
         nx, ny = g1.shape
         is0, is1 = scales if scales is not None else (0, len(kf))
         plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
-        outs = out if out is not None else _maps(nx, ny, is1 - is0, 4)
-        _lib.check(_lib.lib.pfx_wlet_admit_coh_host(plan.handle, _lib.ptr(g1), _lib.ptr(g2), is0, is1,
-                                                    *[_lib.ptr(o) for o in outs]))
+        outs = out if out is not None else _maps(nx, ny, is1 - is0, 4, _OUT_DTYPE)
+        f32 = outs[0].dtype == np.float32
+        if any(o.dtype != outs[0].dtype or o.shape != (nx, ny, is1 - is0) or not o.flags.f_contiguous for o in outs):
+            raise ValueError("output maps must be Fortran-ordered (nx, ny, ns) arrays of one dtype")
+        fn = _lib.lib.pfx_wlet_admit_coh_host_f32 if f32 else _lib.lib.pfx_wlet_admit_coh_host
+        _lib.check(fn(plan.handle, _lib.ptr(g1), _lib.ptr(g2), is0, is1, *[_lib.ptr(o) for o in outs]))
         return tuple(outs)
 
 

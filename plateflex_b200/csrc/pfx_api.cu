@@ -339,8 +339,12 @@ int check_range(const pfx_plan *pl, int is0, int is1)
 
 // h_outs (optional): host destinations of the outputs; each finished scale is copied back on the copy
 // stream while later scales are still being computed.  elems[i] = doubles per cell of output i.
+// h_outs (optional): host destinations of the outputs; each finished scale is copied back on the copy
+// stream while later scales are still being computed.  With d32 / h32 set the epilogue stores float32
+// (each float64 result rounded once) into the device staging arrays d32 and the host receives those.
 int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *d_outs,
-            double *const *h_outs, const int *elems, int nouts, const ShardOut *shards = nullptr)
+            double *const *h_outs, const int *elems, int nouts, const ShardOut *shards = nullptr,
+            float *const *d32 = nullptr, float *const *h32 = nullptr)
 {
     const int ngrids = g2 ? 2 : 1;
     const size_t nxy = (size_t)pl->nx * pl->ny;
@@ -379,18 +383,25 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
             PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, red_stream));
         } else {
             double *o[4] = {nullptr, nullptr, nullptr, nullptr};
-            for (int i = 0; i < nouts && d_outs; i++) o[i] = d_outs[i] + so * elems[i];
+            for (int i = 0; i < nouts && d_outs && !d32; i++) o[i] = d_outs[i] + so * elems[i];
+            for (int i = 0; i < nouts && d32; i++) o[i] = reinterpret_cast<double *>(d32[i] + so * elems[i]);
             ProfScope prof(pl, PFX_KC_REDUCE, red_stream);
             ShardOut sh;
             if (shards) {
                 sh = *shards;
                 sh.scale = is;
             }
-            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream, shards ? &sh : nullptr));
+            PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream, shards ? &sh : nullptr,
+                                    d32 != nullptr));
         }
         pl->launches++;
-        if (overlap || h_outs) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));
-        if (h_outs) {
+        if (overlap || h_outs || h32) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));
+        if (h32) {
+            PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_reduced[b], 0));
+            for (int i = 0; i < nouts; i++)
+                PFX_CUDA(cudaMemcpyAsync(h32[i] + so * elems[i], d32[i] + so * elems[i],
+                                         nxy * elems[i] * sizeof(float), cudaMemcpyDeviceToHost, pl->s_copy));
+        } else if (h_outs) {
             PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_reduced[b], 0));
             for (int i = 0; i < nouts; i++)
                 PFX_CUDA(cudaMemcpyAsync(h_outs[i] + so * elems[i], d_outs[i] + so * elems[i],
@@ -402,7 +413,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_aux));
         PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
     }
-    if (h_outs) {
+    if (h_outs || h32) {
         PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_copy));
         PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
     }
@@ -411,7 +422,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
 
 // Host wrapper: stage the inputs, run, stream the outputs back scale by scale, synchronise.
 int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *outs,
-                 const int *out_elems_per_cell, int nouts)
+                 const int *out_elems_per_cell, int nouts, float *const *outs32 = nullptr)
 {
     DeviceGuard guard(pl->device);
     const size_t nxy = (size_t)pl->nx * pl->ny;
@@ -424,9 +435,14 @@ int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int
         PFX_CUDA(cudaMemcpyAsync(d_g[1], g2, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
     }
     double *d_o[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int i = 0; i < nouts; i++)
+    for (int i = 0; i < nouts && !outs32; i++)
         PFX_CHECK(pl->scratch(2 + i, nxy * nsc * out_elems_per_cell[i] * sizeof(double), (void **)&d_o[i]));
-    PFX_CHECK(run_cwt(pl, mode, d_g[0], d_g[1], is0, is1, d_o, outs, out_elems_per_cell, nouts));
+    float *d_32[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (outs32)
+        for (int i = 0; i < nouts; i++)
+            PFX_CHECK(pl->scratch(6 + i, nxy * nsc * out_elems_per_cell[i] * sizeof(float), (void **)&d_32[i]));
+    PFX_CHECK(run_cwt(pl, mode, d_g[0], d_g[1], is0, is1, d_o, outs32 ? nullptr : outs, out_elems_per_cell, nouts, nullptr,
+                      outs32 ? d_32 : nullptr, outs32));
     PFX_CUDA(cudaStreamSynchronize(pl->stream));
     return PFX_OK;
 }
@@ -538,6 +554,26 @@ int pfx_wlet_admit_coh_host(pfx_plan *pl, const double *topo, const double *grav
     double *outs[4] = {wl_admit, ewl_admit, wl_coh, ewl_coh};
     const int el[4] = {1, 1, 1, 1};
     return run_cwt_host(pl, RED_ADMIT_COH, topo, grav, is0, is1, outs, el, 4);
+}
+
+// ---- float32 outputs: the dtype numpy.f2py gives the reference's REAL arrays ---------------
+int pfx_wlet_scalogram_host_f32(pfx_plan *pl, const double *grid, int is0, int is1, float *wl_sg, float *ewl_sg)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && wl_sg && ewl_sg, "null pointer");
+    float *outs[2] = {wl_sg, ewl_sg};
+    const int el[2] = {1, 1};
+    return run_cwt_host(pl, RED_SCALOGRAM, grid, nullptr, is0, is1, nullptr, el, 2, outs);
+}
+
+int pfx_wlet_admit_coh_host_f32(pfx_plan *pl, const double *topo, const double *grav, int is0, int is1, float *wl_admit,
+                                float *ewl_admit, float *wl_coh, float *ewl_coh)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(topo && grav && wl_admit && ewl_admit && wl_coh && ewl_coh, "null pointer");
+    float *outs[4] = {wl_admit, ewl_admit, wl_coh, ewl_coh};
+    const int el[4] = {1, 1, 1, 1};
+    return run_cwt_host(pl, RED_ADMIT_COH, topo, grav, is0, is1, nullptr, el, 4, outs);
 }
 
 // ---- row-sharded epilogue and IPC-mappable buffers ---------------------------------------

@@ -80,9 +80,9 @@ struct ShardOut {
 //   RED_SCALOGRAM : w1 -> out0 = wl_sg, out1 = ewl_sg                       (cpwt.f90:200-241)
 //   RED_XSCALOGRAM: w1,w2 -> out0 = wl_xsg (complex), out1 = ewl_xsg        (cpwt.f90:250-293)
 //   RED_ADMIT_COH : w1,w2 -> out0..3 = wl_admit, ewl_admit, wl_coh, ewl_coh (cpwt.f90:303-364)
-// Each out* points at the (nx, ny) plane of this scale (x fastest).
+// Each out* points at the (nx, ny) plane of this scale (x fastest); with f32 they are float arrays.
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream, const ShardOut *shards = nullptr);
+                  double *out3, cudaStream_t stream, const ShardOut *shards = nullptr, bool f32 = false);
 
 // K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab.
 int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream);

@@ -70,8 +70,8 @@ struct pfx_plan {
     cudaEvent_t ev_planes[2] = {nullptr, nullptr}, ev_reduced[2] = {nullptr, nullptr}, ev_join = nullptr;
 
     // grow-only scratch used by the _host entry points (inputs / outputs staging)
-    void *d_scratch[8] = {};
-    size_t scratch_bytes[8] = {};
+    void *d_scratch[10] = {};
+    size_t scratch_bytes[10] = {};
 
     std::vector<void *> owned;  // everything to cudaFree on destroy
 

@@ -131,7 +131,17 @@ __device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int 
     return make_double2(w.x * v.scale, w.y * v.scale);
 }
 
-template <int MODE, bool SHARDED>
+// F32: the outputs are float arrays (same element offsets): each float64 result is rounded once on store.
+template <bool F32>
+__device__ __forceinline__ void put(double *base, size_t o, double v)
+{
+    if (F32)
+        reinterpret_cast<float *>(base)[o] = (float)v;
+    else
+        base[o] = v;
+}
+
+template <int MODE, bool SHARDED, bool F32>
 __global__ void __launch_bounds__(128, 4)
     reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
                   double *__restrict__ out2, double *__restrict__ out3, ShardOut sh)
@@ -163,8 +173,8 @@ __global__ void __launch_bounds__(128, 4)
             s[a] = fabs(w.x * w.x + w.y * w.y);  // CABS(w*CONJG(w)), cpwt.f90:224
             tot += s[a];
         }
-        out0[o] = tot * (1.0 / (double)NA);  // cpwt.f90:234
-        out1[o] = jk_sgram(s);
+        put<F32>(out0, o, tot * (1.0 / (double)NA));  // cpwt.f90:234
+        put<F32>(out1, o, jk_sgram(s));
     } else if (MODE == RED_XSCALOGRAM) {
         double xr[NA], xi[NA];
         double tr = 0.0, ti = 0.0;
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(128, 4)
         }
         reinterpret_cast<double2 *>(out0)[o] = make_double2(tr * (1.0 / (double)NA), ti * (1.0 / (double)NA));
         const double er = jk_sgram(xr), ei = jk_sgram(xi);
-        out1[o] = sqrt(er * er + ei * ei);  // cpwt.f90:290
+        put<F32>(out1, o, sqrt(er * er + ei * ei));  // cpwt.f90:290
     } else {
         double s1[NA], s2[NA], xr[NA];
         double t1 = 0.0, t2 = 0.0, tx = 0.0;
@@ -195,12 +205,12 @@ __global__ void __launch_bounds__(128, 4)
         t1 = t1 * (1.0 / (double)NA);  // cpwt.f90:348-350
         t2 = t2 * (1.0 / (double)NA);
         tx = tx * (1.0 / (double)NA);
-        out0[o] = tx / t1;                // cpwt.f90:354
-        out2[o] = (tx * tx) / (t1 * t2);  // cpwt.f90:355
+        put<F32>(out0, o, tx / t1);                // cpwt.f90:354
+        put<F32>(out2, o, (tx * tx) / (t1 * t2));  // cpwt.f90:355
         double ead, eco;
         jk_admit_coh(s1, s2, xr, ead, eco);
-        out1[o] = ead;
-        out3[o] = eco;
+        put<F32>(out1, o, ead);
+        put<F32>(out3, o, eco);
     }
 }
 
@@ -216,26 +226,33 @@ __global__ void crop_kernel(int nx, int ny, PlaneView w, double2 *__restrict__ s
 }  // namespace
 
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream, const ShardOut *shards)
+                  double *out3, cudaStream_t stream, const ShardOut *shards, bool f32)
 {
     dim3 block(128), grid((nx + 127) / 128, ny);
     const ShardOut none;
     if (shards && shards->nshards > 0) {
-        PFX_ARG(mode == RED_ADMIT_COH, "row-sharded output exists for the admittance / coherence epilogue only");
-        reduce_kernel<RED_ADMIT_COH, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr, nullptr,
-                                                                    *shards);
+        PFX_ARG(mode == RED_ADMIT_COH && !f32, "row-sharded output exists for the float64 admittance / coherence epilogue only");
+        reduce_kernel<RED_ADMIT_COH, true, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
+                                                                           nullptr, *shards);
         PFX_CUDA(cudaGetLastError());
         return PFX_OK;
     }
+    PFX_ARG(!(f32 && mode == RED_XSCALOGRAM), "float32 outputs exist for the scalogram and admittance / coherence epilogues");
     switch (mode) {
         case RED_SCALOGRAM:
-            reduce_kernel<RED_SCALOGRAM, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            if (f32)
+                reduce_kernel<RED_SCALOGRAM, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            else
+                reduce_kernel<RED_SCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         case RED_XSCALOGRAM:
-            reduce_kernel<RED_XSCALOGRAM, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            reduce_kernel<RED_XSCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         case RED_ADMIT_COH:
-            reduce_kernel<RED_ADMIT_COH, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            if (f32)
+                reduce_kernel<RED_ADMIT_COH, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            else
+                reduce_kernel<RED_ADMIT_COH, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;
         default:
             set_error("launch_reduce: bad mode %d", mode);

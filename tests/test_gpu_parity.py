@@ -451,3 +451,32 @@ def test_sharded_epilogue_writes_the_row_shard_layout(pf, engine, nshards):
         for m in range(4):
             ref = np.transpose(want[m], (2, 1, 0))[:, r0:r1, :]
             assert np.array_equal(got[m], ref, equal_nan=True), (q, m)
+
+
+def test_float32_outputs_are_the_float64_results_rounded_once(pf, engine):
+    """set_output_dtype(float32): what numpy.f2py returns for the reference's REAL arrays."""
+    from plateflex_b200 import synthetic
+    nx, ny, dx, dy = 33, 47, 10.0, 12.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240031)
+    try:
+        pf.set_output_dtype(np.float64)
+        p64 = pf.Project(grids=[pf.TopoGrid(topo.copy(), dx, dy), pf.BougGrid(grav, dx, dy)])
+        p64.init()
+        p64.wlet_admit_coh()
+        p64.grids[1].wlet_scalogram()
+        pf.set_output_dtype(np.float32)
+        p32 = pf.Project(grids=[pf.TopoGrid(topo.copy(), dx, dy), pf.BougGrid(grav, dx, dy)])
+        p32.init()
+        p32.wlet_admit_coh()
+        p32.grids[1].wlet_scalogram()
+    finally:
+        pf.set_output_dtype(np.float64)
+    for name in ("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"):
+        a32, a64 = getattr(p32, name), getattr(p64, name)
+        assert a32.dtype == np.float32 and a32.flags.f_contiguous and a64.dtype == np.float64
+        assert np.array_equal(a32, a64.astype(np.float32), equal_nan=True), name
+    assert np.array_equal(p32.grids[1].wl_sg, p64.grids[1].wl_sg.astype(np.float32))
+    assert np.array_equal(p32.grids[1].ewl_sg, p64.grids[1].ewl_sg.astype(np.float32))
+    p32.estimate_grid(nn=6)  # the fit takes float32 maps like SciPy takes the reference's
+    p64.estimate_grid(nn=6)
+    assert np.allclose(p32.mean_Te_grid, p64.mean_Te_grid, atol=0.05)
