@@ -87,13 +87,45 @@ def workload(cfg, seed_offset=0):
     return topo, grav, k, pf.cf_wt.k0
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs of its GPU's NUMA node before any pinned host buffer is allocated, so that
+    host<->device copies of several ranks do not all cross one socket's memory (plain plumbing, like numactl)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The sampler is
+    started early (nvidia-smi takes a while to emit its first line on an 8-GPU box); mark_start / mark_end
+    bracket the timed region and the summary uses the samples in between (or the nearest one)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.i0, self.i1 = 0, None
+
+    def mark_start(self):
+        self.i0 = len(self.rows)
+
+    def mark_end(self):
+        time.sleep(0.06)
+        self.i1 = len(self.rows)
 
     def __enter__(self):
         try:
@@ -117,10 +149,12 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        i1 = len(self.rows) if self.i1 is None else self.i1
+        rows = self.rows[self.i0:i1] or self.rows[max(self.i0 - 1, 0):i1 + 1] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -215,6 +249,7 @@ def main():
     from plateflex_b200 import _lib, sharding
 
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -260,13 +295,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
-    launches0 = plan.launch_count()
     times = []
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            step_dev()
         barrier()
+        launches0 = plan.launch_count()
+        clocks.mark_start()
         for _ in range(args.steps):
             flush.zero_()  # L2 flush between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -277,6 +312,7 @@ def main():
             e1.record(stream)
             e1.synchronize()
             times.append(e0.elapsed_time(e1))
+        clocks.mark_end()
         barrier()
     launches = plan.launch_count() - launches0
     # Second timed loop, same steps, with the per-kernel device timers on: an event pair around every
@@ -461,6 +497,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"], "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)",
+                   "cpu_affinity": f"{numa_cpus} CPUs of the GPU's NUMA node" if numa_cpus else "not set",
                    "sharding": ((f"scales over {world} ranks, epilogue stores into peer row shards over NVLink (CUDA IPC)"
                                  if p2p else f"scales over {world} ranks + NCCL all-to-all to row shards") if strong else
                                 (f"{world} independent grid pairs, one per rank" if world > 1 else "single GPU"))},
