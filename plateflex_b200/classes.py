@@ -10,9 +10,10 @@ Mirrored (reference file:line):
   RhocGrid / ZcGrid            classes.py:571-632
   Project                      classes.py:635-1332 (init, wlet_admit_coh, estimate_cell, estimate_grid)
   _lam2k                       classes.py:1757-1828
-Out of scope here (presentation / Bayesian path): the plot_* and save_results
-methods and ``inverse='bayes'``; they raise NotImplementedError with a pointer
-to the reference package.
+  save_results / filter_water_depth   classes.py:538-546, 1621-1754 (host-side post-processing)
+Out of scope here (presentation / Bayesian path): the plot_* methods and
+``inverse='bayes'``; they raise NotImplementedError with a pointer to the
+reference package.
 """
 import sys
 
@@ -24,6 +25,18 @@ from .cpwt import cpwt, fused
 from .flex import conf_flex as cf_f
 
 __all__ = ["Grid", "TopoGrid", "GravGrid", "BougGrid", "FairGrid", "RhocGrid", "ZcGrid", "Project"]
+
+
+def _gaussian(image, sigma=1):
+    """skimage.filters.gaussian as the reference calls it (classes.py:539-541, 1464, 1663) for float
+    images: scipy.ndimage.gaussian_filter with mode='nearest' and truncate=4.0 -- which is what
+    scikit-image itself evaluates; used directly when scikit-image is not installed."""
+    try:
+        from skimage.filters import gaussian
+        return gaussian(image, sigma=sigma)
+    except ImportError:
+        from scipy import ndimage
+        return ndimage.gaussian_filter(np.asarray(image, dtype=np.float64), sigma, mode='nearest', truncate=4.0)
 
 
 def _out_of_scope(name):
@@ -144,9 +157,8 @@ class TopoGrid(Grid):
         self.water_depth = -1. * water_depth
 
     def filter_water_depth(self, sigma=10, returned=False):
-        """classes.py:538-546 (host side, scikit-image)."""
-        from skimage.filters import gaussian
-        water_depth = gaussian(self.data, sigma=sigma)
+        """classes.py:538-546 (host side)."""
+        water_depth = _gaussian(self.data, sigma=sigma)
         water_depth[self.data > 0.] = 0.
         self.water_depth = -1. * water_depth
         if returned:
@@ -384,8 +396,51 @@ class Project(object):
     def plot_results(self, *args, **kwargs):
         _out_of_scope('Project.plot_results')
 
-    def save_results(self, *args, **kwargs):
-        _out_of_scope('Project.save_results')
+    def save_results(self, mean_Te=False, MAP_Te=False, std_Te=False, mean_F=False, MAP_F=False, std_F=False,
+                     mean_a=False, MAP_a=False, std_a=False, chi2=False, mask=False, contours=None, filter=True,
+                     sigma=1, prefix='PlateFlex_'):
+        """classes.py:1621-1754: writes ``<prefix><label>.csv`` with columns x, y, <label> for every
+        requested grid (x = dy*nn*column index, y = dx*nn*row index, row-major order, exactly the
+        reference's ``save_grid``), Gaussian-smoothed first when ``filter`` is set.
+
+        Behaviour kept from the reference, oddities included: the MAP_* grids exist only after a
+        Bayesian estimation (an AttributeError propagates for MAP_Te / MAP_F as it does there); for the
+        alpha grids and chi2 any failure prints the reference's message instead of raising -- and with
+        ``filter=True`` the alpha grids always take that path, because the reference smooths a local
+        variable it never assigned (classes.py:1713-1714, 1723-1724, 1733-1734)."""
+        def save_grid(pars, grid, label, prefix):
+            import pandas as pd
+            xx, yy = np.mgrid[0:pars[0], 0:pars[1]]
+            data = np.array([pars[3] * yy.flatten(), pars[2] * xx.flatten(), np.asarray(grid).flatten()]).T
+            pd.DataFrame(data=data, columns=['x', 'y', label]).to_csv(prefix + label + '.csv', index=False)
+
+        (nnx, nny) = self.mean_Te_grid.shape
+        pars = [nnx, nny, self.dx * self.nn, self.dy * self.nn]
+        if mask:
+            try:
+                save_grid(pars, self.new_mask_grid, 'mask', prefix)
+            except Exception:
+                print('No new mask found. Skipping')
+        if contours is not None:
+            contours = np.array(contours) / self.nn
+        for want, label in ((mean_Te, 'mean_Te'), (MAP_Te, 'MAP_Te'), (std_Te, 'std_Te'), (mean_F, 'mean_F'),
+                            (MAP_F, 'MAP_F'), (std_F, 'std_F')):
+            if want:
+                grid = getattr(self, label + '_grid')
+                save_grid(pars, _gaussian(grid, sigma=sigma) if filter else grid, label, prefix)
+        for want, label in ((mean_a, 'mean_a'), (MAP_a, 'MAP_a'), (std_a, 'std_a')):
+            if want:
+                try:
+                    if filter:
+                        raise UnboundLocalError(label + '_grid')  # the reference's unassigned local
+                    save_grid(pars, getattr(self, label + '_grid'), label, prefix)
+                except Exception:
+                    print("parameter 'alpha' was not estimated")
+        if chi2:
+            try:
+                save_grid(pars, _gaussian(self.chi2_grid, sigma=sigma) if filter else self.chi2_grid, 'chi2', prefix)
+            except Exception:
+                print("parameter 'chi2' was not estimated")
 
 
 def _lam2k(nx, ny, dx, dy, p=0.85):
