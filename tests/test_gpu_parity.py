@@ -277,7 +277,7 @@ def test_wlet_scalogram_paths_agree_like_the_reference_docstring(pf, engine):
     assert np.allclose(g1.wl_sg, g2.wl_sg, rtol=1e-12) and np.allclose(g1.ewl_sg, g2.ewl_sg, rtol=1e-10)
 
 
-@pytest.mark.parametrize("n", [1024])
+@pytest.mark.parametrize("n", [1024, 2048])
 def test_full_size_properties(pf, engine, n):
     """BASELINE configs[1] size (1024^2, 5 km): properties that need no oracle.
     Linearity of the transform, scalogram == azimuth mean of |W|^2, admittance of a scaled copy."""
@@ -297,6 +297,31 @@ def test_full_size_properties(pf, engine, n):
     adm, eadm, coh, ecoh = fused.wlet_admit_coh(topo, 0.05 * topo, 5.0, 5.0, k)
     assert np.allclose(adm, 0.05, rtol=1e-10) and np.allclose(coh, 1.0, rtol=1e-10)
     assert np.abs(eadm).max() < 1e-10 and np.abs(ecoh).max() < 1e-10
+
+
+def test_c3_size_properties_without_oracle(pf):
+    """BASELINE configs[2] size (4096^2, padded 8192^2: four parts per line in the second-generation kernels),
+    fused path only: gravity = c * topography must give admittance c, coherence 1 and vanishing jackknife errors
+    at every cell; the scalogram of a sum of two fields is checked against its parts through the parallelogram
+    identity |a+b|^2 + |a-b|^2 = 2|a|^2 + 2|b|^2 (azimuth means are linear in |W|^2)."""
+    from plateflex_b200 import _lib, classes, synthetic
+    from plateflex_b200.cpwt import fused
+    n = 4096
+    _lib.clear_plans()
+    topo, grav = synthetic.make_pair(n, n, 5.0, 5.0, seed=20240000 + n)
+    k = classes._lam2k(n, n, 5.0, 5.0)[1][:20][[0, 10, 19]]
+    adm, eadm, coh, ecoh = fused.wlet_admit_coh(topo, -0.07 * topo, 5.0, 5.0, k)
+    assert np.allclose(adm, -0.07, rtol=1e-10) and np.allclose(coh, 1.0, rtol=1e-10)
+    assert np.abs(eadm).max() < 1e-10 and np.abs(ecoh).max() < 1e-10
+    del adm, eadm, coh, ecoh
+    sa, _ = fused.wlet_scalogram(topo, 5.0, 5.0, k)
+    sb, _ = fused.wlet_scalogram(40.0 * grav, 5.0, 5.0, k)
+    sp, _ = fused.wlet_scalogram(topo + 40.0 * grav, 5.0, 5.0, k)
+    sm, _ = fused.wlet_scalogram(topo - 40.0 * grav, 5.0, 5.0, k)
+    for s in range(3):
+        lhs, rhs = sp[..., s] + sm[..., s], 2.0 * (sa[..., s] + sb[..., s])
+        assert np.abs(lhs - rhs).max() <= 1e-11 * rhs.max()
+    _lib.clear_plans()
 
 
 @pytest.mark.skipif(len(ENGINES) < 2, reason="needs both engines")
