@@ -144,6 +144,7 @@ int pfx_wlet_admit_coh_dev(pfx_plan *plan, const double *topo_dev, const double 
 /* The reference's REAL arrays reach Python as float32 (numpy.f2py).  These forms compute in
  * float64 like everything else and round each result once on the device, halving the device-to-host
  * copy that bounds the host-pointer calls (671 MB -> 336 MB per 1024^2 x 20 transform). */
+int pfx_wlet_transform_host_c64(pfx_plan *plan, const double *grid, int is0, int is1, float *cube /* complex64 */);
 int pfx_wlet_scalogram_host_f32(pfx_plan *plan, const double *grid, int is0, int is1, float *wl_sg, float *ewl_sg);
 int pfx_wlet_admit_coh_host_f32(pfx_plan *plan, const double *topo, const double *grav, int is0, int is1,
                                 float *wl_admit, float *ewl_admit, float *wl_coh, float *ewl_coh);

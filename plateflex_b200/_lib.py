@@ -65,6 +65,7 @@ _SIGS = {
     "pfx_wlet_xscalogram_dev": ([_vp, _vp, _vp, _i, _i, _vp, _vp], _i),
     "pfx_wlet_admit_coh_host": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_wlet_admit_coh_dev": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+    "pfx_wlet_transform_host_c64": ([_vp, _vp, _i, _i, _vp], _i),
     "pfx_wlet_scalogram_host_f32": ([_vp, _vp, _i, _i, _vp, _vp], _i),
     "pfx_wlet_admit_coh_host_f32": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_wlet_admit_coh_sharded_dev": ([_vp, _vp, _vp, _i, _i, _i, _vp], _i),

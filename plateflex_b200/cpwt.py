@@ -88,8 +88,10 @@ class _Cpwt:
         kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
         nx, ny = g.shape
         plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
-        out = np.empty((nx, ny, _lib.NA, len(kf)), dtype=np.complex128, order="F")
-        _lib.check(_lib.lib.pfx_wlet_transform_host(plan.handle, _lib.ptr(g), 0, len(kf), _lib.ptr(out)))
+        c64 = _OUT_DTYPE == np.float32  # complex64 cube, as numpy.f2py returns the reference's COMPLEX array
+        out = np.empty((nx, ny, _lib.NA, len(kf)), dtype=np.complex64 if c64 else np.complex128, order="F")
+        fn = _lib.lib.pfx_wlet_transform_host_c64 if c64 else _lib.lib.pfx_wlet_transform_host
+        _lib.check(fn(plan.handle, _lib.ptr(g), 0, len(kf), _lib.ptr(out)))
         return out
 
     def wlet_scalogram(self, wl_trans):

@@ -380,7 +380,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         }
         if (mode == OUT_CUBE) {
             ProfScope prof(pl, PFX_KC_CROP, red_stream);
-            PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, red_stream));
+            PFX_CHECK(launch_crop(pl->nx, pl->ny, v1, reinterpret_cast<double2 *>(d_outs[0]) + so * PFX_NA, false, red_stream));
         } else {
             double *o[4] = {nullptr, nullptr, nullptr, nullptr};
             for (int i = 0; i < nouts && d_outs && !d32; i++) o[i] = d_outs[i] + so * elems[i];
@@ -461,20 +461,24 @@ int pfx_wlet_transform_dev(pfx_plan *pl, const double *grid, int is0, int is1, d
     return run_cwt(pl, OUT_CUBE, grid, nullptr, is0, is1, outs, nullptr, el, 1);
 }
 
-int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, double *cube)
+// Cube to the host, one scale slab (nx*ny*11 complex) at a time through two device slabs: the whole cube need
+// not fit on the device, and the transform of scale s+1 runs while slab s crosses PCIe (classes.py:225 keeps
+// the full cube in host memory).  c64: slabs and host cube are complex64, the dtype
+// numpy.f2py gives the reference's COMPLEX array.
+static int transform_to_host(pfx_plan *pl, const double *grid, int is0, int is1, void *cube, bool c64)
 {
-    PFX_CHECK(check_range(pl, is0, is1));
-    PFX_ARG(grid && cube, "null pointer");
-    // One scale slab (nx*ny*11 complex) at a time: the whole cube need not fit on the device.
     DeviceGuard guard(pl->device);
-    const size_t nxy = (size_t)pl->nx * pl->ny, slab = nxy * PFX_NA * 2;
-    double *d_g = nullptr, *d_slab = nullptr;
+    const size_t nxy = (size_t)pl->nx * pl->ny, slab_el = nxy * PFX_NA;
+    const size_t slab_bytes = slab_el * (c64 ? sizeof(float2) : sizeof(double2));
+    double *d_g = nullptr;
+    void *d_slab[2] = {nullptr, nullptr};
     PFX_CHECK(pl->scratch(0, nxy * sizeof(double), (void **)&d_g));
-    PFX_CHECK(pl->scratch(2, slab * sizeof(double), (void **)&d_slab));
+    PFX_CHECK(pl->scratch(2, slab_bytes, &d_slab[0]));
+    PFX_CHECK(pl->scratch(3, slab_bytes, &d_slab[1]));
     PFX_CUDA(cudaMemcpyAsync(d_g, grid, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
     PFX_CHECK(forward_spectrum(pl, d_g, 0));
     if (pl->engine == PFX_ENGINE_PRUNED) PFX_CHECK(pruned_prepare(pl, 1));
-    for (int is = is0; is < is1; is++) {
+    auto enqueue = [&](int is, int b) -> int {  // planes of scale `is`, cropped into slab b
         PlaneView v;
         if (pl->engine == PFX_ENGINE_DENSE) {
             PFX_CHECK(dense_scale_planes(pl, is, 1));
@@ -483,16 +487,42 @@ int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, 
             PFX_CHECK(pruned_scale_planes(pl, is, 1));
             v = pruned_view(pl, 0);
         }
-        {
-            ProfScope prof(pl, PFX_KC_CROP, pl->stream);
-            PFX_CHECK(launch_crop(pl->nx, pl->ny, v, reinterpret_cast<double2 *>(d_slab), pl->stream));
-        }
+        ProfScope prof(pl, PFX_KC_CROP, pl->stream);
+        PFX_CHECK(launch_crop(pl->nx, pl->ny, v, d_slab[b], c64, pl->stream));
         pl->launches++;
-        PFX_CUDA(cudaMemcpyAsync(cube + (size_t)(is - is0) * slab, d_slab, slab * sizeof(double), cudaMemcpyDeviceToHost,
-                                 pl->stream));
-        PFX_CUDA(cudaStreamSynchronize(pl->stream));
+        PFX_CUDA(cudaEventRecord(pl->ev_planes[b], pl->stream));
+        return PFX_OK;
+    };
+    PFX_CHECK(enqueue(is0, 0));
+    for (int is = is0; is < is1; is++) {
+        const int b = (is - is0) & 1;
+        if (is + 1 < is1) {
+            // slab b^1 was last read by the copy of scale is-1
+            if (is - is0 >= 1) PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_reduced[b ^ 1], 0));
+            PFX_CHECK(enqueue(is + 1, b ^ 1));
+        }
+        PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_planes[b], 0));
+        PFX_CUDA(cudaMemcpyAsync(static_cast<char *>(cube) + (size_t)(is - is0) * slab_bytes, d_slab[b], slab_bytes,
+                                 cudaMemcpyDeviceToHost, pl->s_copy));
+        PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], pl->s_copy));
     }
+    PFX_CUDA(cudaStreamSynchronize(pl->s_copy));
+    PFX_CUDA(cudaStreamSynchronize(pl->stream));
     return PFX_OK;
+}
+
+int pfx_wlet_transform_host(pfx_plan *pl, const double *grid, int is0, int is1, double *cube)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && cube, "null pointer");
+    return transform_to_host(pl, grid, is0, is1, cube, false);
+}
+
+int pfx_wlet_transform_host_c64(pfx_plan *pl, const double *grid, int is0, int is1, float *cube)
+{
+    PFX_CHECK(check_range(pl, is0, is1));
+    PFX_ARG(grid && cube, "null pointer");
+    return transform_to_host(pl, grid, is0, is1, cube, true);
 }
 
 int pfx_wlet_scalogram_dev(pfx_plan *pl, const double *grid, int is0, int is1, double *wl_sg, double *ewl_sg)

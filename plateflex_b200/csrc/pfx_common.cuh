@@ -84,7 +84,7 @@ struct ShardOut {
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
                   double *out3, cudaStream_t stream, const ShardOut *shards = nullptr, bool f32 = false);
 
-// K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab.
-int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream);
+// K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab of double2, or float2 with c64.
+int launch_crop(int nx, int ny, PlaneView w, void *slab, bool c64, cudaStream_t stream);
 
 }  // namespace pfx

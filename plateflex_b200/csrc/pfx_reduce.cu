@@ -214,13 +214,19 @@ __global__ void __launch_bounds__(128, 4)
     }
 }
 
-__global__ void crop_kernel(int nx, int ny, PlaneView w, double2 *__restrict__ slab)
+template <bool C64>
+__global__ void crop_kernel(int nx, int ny, PlaneView w, void *__restrict__ slab)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     const int p = blockIdx.z;
     if (i >= nx) return;
-    slab[((size_t)p * ny + j) * nx + i] = load_w(w, p, i, j, load_z(w, i, j));
+    const double2 v = load_w(w, p, i, j, load_z(w, i, j));
+    const size_t o = ((size_t)p * ny + j) * nx + i;
+    if (C64)
+        static_cast<float2 *>(slab)[o] = make_float2((float)v.x, (float)v.y);
+    else
+        static_cast<double2 *>(slab)[o] = v;
 }
 
 }  // namespace
@@ -262,10 +268,13 @@ int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *
     return PFX_OK;
 }
 
-int launch_crop(int nx, int ny, PlaneView w, double2 *slab, cudaStream_t stream)
+int launch_crop(int nx, int ny, PlaneView w, void *slab, bool c64, cudaStream_t stream)
 {
     dim3 block(128), grid((nx + 127) / 128, ny, PFX_NA);
-    crop_kernel<<<grid, block, 0, stream>>>(nx, ny, w, slab);
+    if (c64)
+        crop_kernel<true><<<grid, block, 0, stream>>>(nx, ny, w, slab);
+    else
+        crop_kernel<false><<<grid, block, 0, stream>>>(nx, ny, w, slab);
     PFX_CUDA(cudaGetLastError());
     return PFX_OK;
 }

@@ -500,6 +500,14 @@ def test_float32_outputs_are_the_float64_results_rounded_once(pf, engine):
         a32, a64 = getattr(p32, name), getattr(p64, name)
         assert a32.dtype == np.float32 and a32.flags.f_contiguous and a64.dtype == np.float64
         assert np.array_equal(a32, a64.astype(np.float32), equal_nan=True), name
+    p64.grids[0].wlet_transform()
+    pf.set_output_dtype(np.float32)
+    try:
+        p32.grids[0].wlet_transform()
+    finally:
+        pf.set_output_dtype(np.float64)
+    assert p32.grids[0].wl_trans.dtype == np.complex64 and p32.grids[0].wl_trans.flags.f_contiguous
+    assert np.array_equal(p32.grids[0].wl_trans, p64.grids[0].wl_trans.astype(np.complex64))
     assert np.array_equal(p32.grids[1].wl_sg, p64.grids[1].wl_sg.astype(np.float32))
     assert np.array_equal(p32.grids[1].ewl_sg, p64.grids[1].ewl_sg.astype(np.float32))
     p32.estimate_grid(nn=6)  # the fit takes float32 maps like SciPy takes the reference's
