@@ -58,22 +58,36 @@ int pfx_plan::alloc(void **p, size_t bytes)
 int pfx_plan::scratch(int slot, size_t bytes, void **p)
 {
     if (bytes > scratch_bytes[slot]) {
-        if (d_scratch[slot]) {
-            PFX_CUDA(cudaStreamSynchronize(stream));
-            PFX_CUDA(cudaFree(d_scratch[slot]));
-            device_bytes -= scratch_bytes[slot];
-            d_scratch[slot] = nullptr;
-            scratch_bytes[slot] = 0;
-        }
+        auto release = [&](int s) {
+            if (d_scratch[s]) {
+                cudaFree(d_scratch[s]);
+                device_bytes -= scratch_bytes[s];
+                d_scratch[s] = nullptr;
+                scratch_bytes[s] = 0;
+            }
+        };
+        PFX_CUDA(cudaStreamSynchronize(stream));
+        release(slot);
         cudaError_t e = cudaMalloc(&d_scratch[slot], bytes);
         if (e != cudaSuccess) {
+            // Staging buffers of earlier calls (other output dtypes, other entry points) are only a cache:
+            // give back those not handed out in the current call and try once more.
             cudaGetLastError();
+            PFX_CUDA(cudaDeviceSynchronize());
+            for (int s = 0; s < (int)(sizeof d_scratch / sizeof d_scratch[0]); s++)
+                if (scratch_call[s] != call_id) release(s);
+            e = cudaMalloc(&d_scratch[slot], bytes);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            d_scratch[slot] = nullptr;
             set_error("device scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
             return PFX_ERR_OOM;
         }
         scratch_bytes[slot] = bytes;
         device_bytes += bytes;
     }
+    scratch_call[slot] = call_id;
     *p = d_scratch[slot];
     return PFX_OK;
 }
@@ -425,6 +439,7 @@ int run_cwt_host(pfx_plan *pl, int mode, const double *g1, const double *g2, int
                  const int *out_elems_per_cell, int nouts, float *const *outs32 = nullptr)
 {
     DeviceGuard guard(pl->device);
+    pl->call_id++;
     const size_t nxy = (size_t)pl->nx * pl->ny;
     const int nsc = is1 - is0;
     double *d_g[2] = {nullptr, nullptr};
@@ -468,6 +483,7 @@ int pfx_wlet_transform_dev(pfx_plan *pl, const double *grid, int is0, int is1, d
 static int transform_to_host(pfx_plan *pl, const double *grid, int is0, int is1, void *cube, bool c64)
 {
     DeviceGuard guard(pl->device);
+    pl->call_id++;
     const size_t nxy = (size_t)pl->nx * pl->ny, slab_el = nxy * PFX_NA;
     const size_t slab_bytes = slab_el * (c64 ? sizeof(float2) : sizeof(double2));
     double *d_g = nullptr;

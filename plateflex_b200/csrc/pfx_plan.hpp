@@ -72,6 +72,8 @@ struct pfx_plan {
     // grow-only scratch used by the _host entry points (inputs / outputs staging)
     void *d_scratch[10] = {};
     size_t scratch_bytes[10] = {};
+    unsigned long scratch_call[10] = {};  // host call that last used the slot
+    unsigned long call_id = 0;
 
     std::vector<void *> owned;  // everything to cudaFree on destroy
 
