@@ -734,7 +734,7 @@ static int cube_reduce_host(int device, int mode, int nx, int ny, int ns, const 
     for (int is = 0; is < ns && rc == PFX_OK; is++) {
         CUBE_CUDA(cudaMemcpyAsync(d_w[0], w1 + 2 * slab * is, slab * sizeof(double2), cudaMemcpyHostToDevice, 0));
         if (w2) CUBE_CUDA(cudaMemcpyAsync(d_w[1], w2 + 2 * slab * is, slab * sizeof(double2), cudaMemcpyHostToDevice, 0));
-        PlaneView v1{d_w[0], nxy, nx, 0, 0, 1.0, nullptr, {}}, v2{w2 ? d_w[1] : d_w[0], nxy, nx, 0, 0, 1.0, nullptr, {}};
+        PlaneView v1{d_w[0], nxy, nx, 0, 0, 1.0, nullptr, 0, {}}, v2{w2 ? d_w[1] : d_w[0], nxy, nx, 0, 0, 1.0, nullptr, 0, {}};
         rc = launch_reduce(mode, nx, ny, v1, v2, d_o[0], d_o[1], d_o[2], d_o[3], 0);
         if (rc != PFX_OK) break;
         CUBE_CUDA(cudaMemcpyAsync(o0 + nxy * e0 * is, d_o[0], nxy * e0 * sizeof(double), cudaMemcpyDeviceToHost, 0));

@@ -50,8 +50,9 @@ void set_error(const char *fmt, ...);
 // The dense engine hands over whole padded cuFFT planes (off = +1: the one-sample
 // shift of cpwt.f90:173-185, scale = 1/(nnx*nny) of cpwt.f90:177); the pruned engine
 // and the cube-input forms hand over compact (nx, ny) planes.  When zc is set the planes hold only the
-// main Gaussian term of the daughter and the coefficient is  W[p](i,j) - ce[p] * zc[j*ld + i]  (the
-// scale- and azimuth-independent admissibility term of cpwt_sub.f90:93-94, see pfx_cwt_pruned.cu).
+// main Gaussian term of the daughter and the coefficient is  W[p](i,j) - ce[p] * Z(i,j)  with the real
+// Z = zc[j*ld + i].x or .y (zsel: the grid)  -- the scale- and azimuth-independent admissibility term of
+// cpwt_sub.f90:93-94, see pfx_cwt_pruned.cu.
 struct PlaneView {
     const double2 *base;
     size_t plane_stride;
@@ -59,6 +60,7 @@ struct PlaneView {
     int off_i, off_j;
     double scale;
     const double2 *zc;
+    int zsel;
     double ce[PFX_NA];
 };
 

@@ -247,6 +247,7 @@ PlaneView dense_view(const pfx_plan *pl, int g)
     v.off_j = 1;
     v.scale = 1.0 / (double)P;
     v.zc = nullptr;
+    v.zsel = 0;
     for (int ia = 0; ia < PFX_NA; ia++) v.ce[ia] = 0.0;
     return v;
 }

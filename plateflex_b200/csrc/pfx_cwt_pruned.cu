@@ -74,39 +74,41 @@ __global__ void twiddle_kernel(int logN, int logL, const int *lo, const double2 
     tw[((size_t)ia << logN) + e] = root[idx];
 }
 
-// Admissibility term on the y-fastest layout: plane[g][a][b] = exp(-kx^2/2) exp(-ky^2/2) X_g[a][b]   (cpwt_sub.f90:93)
+// Admissibility term on the y-fastest layout (cpwt_sub.f90:93).  exp(-kx^2/2) exp(-ky^2/2) is real and even and
+// the spectra of the (real) grids are Hermitian, so the transform of the product is real: both grids share ONE
+// complex plane,  plane[a][b] = G (X_0 + i X_1)[a][b],  whose inverse transform is Z_0 + i Z_1.
 __global__ void zmul_kernel(int NX, int NY, const double2 *__restrict__ s0, const double2 *__restrict__ s1,
-                            const double *__restrict__ u2, const double *__restrict__ v2, double2 *planes)
+                            const double *__restrict__ u2, const double *__restrict__ v2, double2 *plane)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
     if (b >= NY) return;
-    const size_t o = (size_t)a * NY + b, P = (size_t)NX * NY;
+    const size_t o = (size_t)a * NY + b;
     const double w = u2[a] * v2[b];
-    const double2 x0 = s0[o];
-    planes[o] = make_double2(w * x0.x, w * x0.y);
+    double2 x = s0[o];
     if (s1) {
         const double2 x1 = s1[o];
-        planes[P + o] = make_double2(w * x1.x, w * x1.y);
+        x = make_double2(x.x - x1.y, x.y + x1.x);
     }
+    plane[o] = make_double2(w * x.x, w * x.y);
 }
 
-// zc[g][j][i] = scale * plane[g][i+1][j+1]: crop with the one-sample shift, transposed to the x-fastest
-// layout of the coefficient planes through a 32 x 32 shared-memory tile
+// zc[j][i] = scale * plane[i+1][j+1] = (Z_0, Z_1)(i, j): crop with the one-sample shift, transposed to the
+// x-fastest layout of the coefficient planes through a 32 x 32 shared-memory tile
 __global__ void __launch_bounds__(256)
-    zcrop_kernel(int nx, int ny, int NY, size_t P, double scale, const double2 *__restrict__ planes, double2 *zc)
+    zcrop_kernel(int nx, int ny, int NY, double scale, const double2 *__restrict__ plane, double2 *zc)
 {
     __shared__ double2 tile[32][33];
-    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32, g = blockIdx.z;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int i = i0 + r, j = j0 + threadIdx.x;
-        if (i < nx && j < ny) tile[r][threadIdx.x] = planes[g * P + (size_t)(i + 1) * NY + (j + 1)];
+        if (i < nx && j < ny) tile[r][threadIdx.x] = plane[(size_t)(i + 1) * NY + (j + 1)];
     }
     __syncthreads();
     for (int c = threadIdx.y; c < 32; c += 8) {
         const int i = i0 + threadIdx.x, j = j0 + c;
         if (i < nx && j < ny) {
             const double2 v = tile[threadIdx.x][c];
-            zc[((size_t)g * ny + j) * nx + i] = make_double2(v.x * scale, v.y * scale);
+            zc[(size_t)j * nx + i] = make_double2(v.x * scale, v.y * scale);
         }
     }
 }
@@ -150,8 +152,8 @@ struct PrunedState {
     double *tabu = nullptr, *tabv = nullptr;
     double2 *twa = nullptr, *twb = nullptr;
     double2 *T = nullptr, *W = nullptr, *Wbuf[2] = {nullptr, nullptr}, *zc = nullptr, *zplanes = nullptr;
-    cufftHandle fft_z[2] = {0, 0};
-    bool fft_z_ok[2] = {false, false};
+    cufftHandle fft_z = 0;
+    bool fft_z_ok = false;
     size_t smem1 = 0, smem2 = 0;
     int cpc = 2;
     int ctas_per_transform = 128;
@@ -288,8 +290,8 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CHECK(dalloc((void **)&st->T, 2 * PFX_NA * kamax_all * ny * sizeof(double2)));
     for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Wbuf[b], 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
     st->W = st->Wbuf[0];
-    PFX_CHECK(dalloc((void **)&st->zc, 2 * (size_t)nx * ny * sizeof(double2)));
-    PFX_CHECK(dalloc((void **)&st->zplanes, 2 * P * sizeof(double2)));
+    PFX_CHECK(dalloc((void **)&st->zc, (size_t)nx * ny * sizeof(double2)));
+    PFX_CHECK(dalloc((void **)&st->zplanes, P * sizeof(double2)));
 
     root_kernel<<<(NX + 255) / 256, 256, 0, pl->stream>>>(NX, st->rootx);
     root_kernel<<<(NY + 255) / 256, 256, 0, pl->stream>>>(NY, st->rooty);
@@ -332,15 +334,15 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CUDA(cudaGetLastError());
     PFX_CUDA(cudaStreamSynchronize(pl->stream));  // h_lo / h_k0 go out of scope
 
-    // dense inverse plans for the admissibility term (1 or 2 planes), y-fastest layout
+    // dense inverse plan for the admissibility term (one plane serves both grids), y-fastest layout
     int n[2] = {NX, NY};
     size_t need = pl->fft_work_bytes;
-    for (int g = 0; g < 2; g++) {
+    {
         size_t ws = 0;
-        PFX_CUFFT(cufftCreate(&st->fft_z[g]));
-        st->fft_z_ok[g] = true;
-        PFX_CUFFT(cufftSetAutoAllocation(st->fft_z[g], 0));
-        PFX_CUFFT(cufftMakePlanMany(st->fft_z[g], 2, n, nullptr, 1, (int)P, nullptr, 1, (int)P, CUFFT_Z2Z, g + 1, &ws));
+        PFX_CUFFT(cufftCreate(&st->fft_z));
+        st->fft_z_ok = true;
+        PFX_CUFFT(cufftSetAutoAllocation(st->fft_z, 0));
+        PFX_CUFFT(cufftMakePlanMany(st->fft_z, 2, n, nullptr, 1, (int)P, nullptr, 1, (int)P, CUFFT_Z2Z, 1, &ws));
         need = std::max(need, ws);
     }
     if (need > pl->fft_work_bytes) {
@@ -350,7 +352,7 @@ int plan_init_pruned(pfx_plan *pl)
         pl->fft_work_bytes = need;
         PFX_CUFFT(cufftSetWorkArea(pl->fft_fwd, pl->d_fft_work));
     }
-    for (int g = 0; g < 2; g++) PFX_CUFFT(cufftSetWorkArea(st->fft_z[g], pl->d_fft_work));
+    PFX_CUFFT(cufftSetWorkArea(st->fft_z, pl->d_fft_work));
 
     for (int is = 0; is < ns; is++) {
         const ScaleDesc &sd = st->sd[is];
@@ -375,8 +377,7 @@ void plan_free_pruned(pfx_plan *pl)
 {
     PrunedState *st = state_of(pl);
     if (!st) return;
-    for (int g = 0; g < 2; g++)
-        if (st->fft_z_ok[g]) cufftDestroy(st->fft_z[g]);
+    if (st->fft_z_ok) cufftDestroy(st->fft_z);
     cudaStreamSynchronize(pl->stream);
     for (auto &pb : st->owned) {
         cudaFree(pb.first);
@@ -386,7 +387,7 @@ void plan_free_pruned(pfx_plan *pl)
     pl->pruned = nullptr;
 }
 
-// Once per set of forward spectra: Z = crop(IFFT2(u2*v2*X))/P for each grid.
+// Once per set of forward spectra: (Z_0, Z_1) = crop(IFFT2(u2*v2*(X_0 + i X_1)))/P.
 int pruned_prepare(pfx_plan *pl, int ngrids)
 {
     PrunedState *st = state_of(pl);
@@ -395,11 +396,11 @@ int pruned_prepare(pfx_plan *pl, int ngrids)
     zmul_kernel<<<dim3((pl->NY + 255) / 256, pl->NX), 256, 0, pl->stream>>>(
         pl->NX, pl->NY, pl->d_spec[0], ngrids == 2 ? pl->d_spec[1] : nullptr, pl->d_u2, pl->d_v2, st->zplanes);
     PFX_CUDA(cudaGetLastError());
-    cufftHandle h = st->fft_z[ngrids - 1];
+    cufftHandle h = st->fft_z;
     PFX_CUFFT(cufftSetStream(h, pl->stream));
     PFX_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *)st->zplanes, (cufftDoubleComplex *)st->zplanes, CUFFT_INVERSE));
-    zcrop_kernel<<<dim3((pl->nx + 31) / 32, (pl->ny + 31) / 32, ngrids), dim3(32, 8), 0, pl->stream>>>(
-        pl->nx, pl->ny, pl->NY, P, 1.0 / (double)P, st->zplanes, st->zc);
+    zcrop_kernel<<<dim3((pl->nx + 31) / 32, (pl->ny + 31) / 32), dim3(32, 8), 0, pl->stream>>>(
+        pl->nx, pl->ny, pl->NY, 1.0 / (double)P, st->zplanes, st->zc);
     PFX_CUDA(cudaGetLastError());
     pl->launches += 3;
     return PFX_OK;
@@ -492,7 +493,8 @@ PlaneView pruned_view(const pfx_plan *pl, int g)
     v.off_i = 0;
     v.off_j = 0;
     v.scale = 1.0;
-    v.zc = st->zc + (size_t)g * nxy;  // W = main term - c*E*Z (cpwt_sub.f90:93-94)
+    v.zc = st->zc;  // W = main term - c*E*Z_g (cpwt_sub.f90:93-94), Z real: zc[j][i] = (Z_0, Z_1)
+    v.zsel = g;
     for (int ia = 0; ia < PFX_NA; ia++) v.ce[ia] = st->cur_ce[ia];
     return v;
 }

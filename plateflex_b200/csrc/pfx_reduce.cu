@@ -119,15 +119,16 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
     eco = jk_spread(co2);
 }
 
+// the (real) admissibility terms of both grids at cell (i, j)
 __device__ __forceinline__ double2 load_z(const PlaneView &v, int i, int j)
 {
     return v.zc ? __ldg(v.zc + (size_t)j * v.ld + i) : make_double2(0.0, 0.0);
 }
 
-__device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int j, double2 z)
+__device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int j, double2 zz)
 {
     const double2 w = __ldg(v.base + (size_t)p * v.plane_stride + (size_t)(j + v.off_j) * v.ld + (i + v.off_i));
-    if (v.zc) return make_double2(w.x - v.ce[p] * z.x, w.y - v.ce[p] * z.y);
+    if (v.zc) return make_double2(w.x - v.ce[p] * (v.zsel ? zz.y : zz.x), w.y);
     return make_double2(w.x * v.scale, w.y * v.scale);
 }
 
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(128, 4)
         out3 = out2 + map_stride;
         o = ((size_t)sh.scale * rq + jl) * nx + i;
     }
-    const double2 z1 = load_z(w1, i, j);
-    const double2 z2 = (MODE == RED_SCALOGRAM) ? z1 : load_z(w2, i, j);
+    const double2 z1 = load_z(w1, i, j);  // both grids' terms live in one array
+    const double2 z2 = z1;
 
     if (MODE == RED_SCALOGRAM) {
         double s[NA];
