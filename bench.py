@@ -453,11 +453,14 @@ def main():
         cells = (nx - 1) * (ny - 1)
         fit_ms = float(tf.mean().item())
         te_map = fo[0][:nx * myl.value].cpu().numpy().reshape(myl.value, nx)
-        stat = st[:nx * myl.value].cpu().numpy().reshape(myl.value, nx)
+        raw = st[:nx * myl.value].cpu().numpy().reshape(myl.value, nx)
+        stat, nfev = raw & 0xff, raw >> 8  # low byte: status, upper bits: model evaluations of the cell
         fitted = stat > 0
         fit = {"cells_per_s": cells / (fit_ms * 1e-3), "ms": fit_ms, "cells": cells, "atype": "joint",
                "alph": bool(alph), "converged_frac": float((stat == 1).sum() / max(fitted.sum(), 1)),
                "median_Te_km": float(np.median(te_map[fitted])) if fitted.any() else None, "true_Te_km": cfg["Te"],
+               "nfev_mean": float(nfev[fitted].mean()) if fitted.any() else None,
+               "nfev_max": int(nfev[fitted].max()) if fitted.any() else None,
                "sharding": f"rows over {world} rank(s)" if strong else "none"}
 
     if rank != 0:

@@ -200,8 +200,9 @@ int pfx_flex_xspec_host(int device, const pfx_flex_conf *conf, const double *k, 
  * (classes.py:1218-1219); outputs are (mx, my) = (nx/nn, ny/nn) maps, x
  * fastest, zero where not fitted (classes.py:1189-1204).  out_alpha /
  * out_alpha_std may be NULL when alph == 0.  status (int32, may be NULL):
- * 0 not fitted, 1 converged, 2 iteration limit, 3 bad data (sigma<=0 / NaN:
- * where SciPy would raise, estimate.py:274 -> ValueError).
+ * low byte 0 not fitted, 1 converged, 2 iteration limit, 3 bad data (sigma<=0 / NaN:
+ * where SciPy would raise, estimate.py:274 -> ValueError); the upper 24 bits hold the
+ * number of model evaluations the cell used (least_squares' nfev).
  */
 int pfx_l2_fit_host(int device, const pfx_flex_conf *conf, const double *k, int ns, int nx, int ny,
                     const double *wl_admit, const double *ewl_admit, const double *wl_coh, const double *ewl_coh,

@@ -21,6 +21,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "pfx_flex.cuh"
 
@@ -46,6 +47,8 @@ struct FitArgs {
     int cj0;     // global index of the first output row of this shard (else 0)
     double *o_te, *o_te_std, *o_f, *o_f_std, *o_a, *o_a_std, *o_chi2;
     int32_t *status;
+    unsigned long long *counter;  // lane-persistent kernel: next cell to hand out (zeroed before the launch)
+    int fetch_min;                // ... lanes of a warp wait until this many of them need a new cell
 };
 
 template <int NP>
@@ -400,7 +403,7 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask)
 // termination status (1 gtol, 2 ftol, 3 xtol, 4 both), -1 when max_nfev was reached, -3 when the
 // residuals are not finite at the starting point; x / cur hold the final point.
 template <int NP, class Eval>
-__device__ __forceinline__ int trf_minimize(const Eval &evaluate, int m, double (&x)[NP], Normal<NP> &cur)
+__device__ __forceinline__ int trf_minimize(const Eval &evaluate, int m, double (&x)[NP], Normal<NP> &cur, int &nfev_out)
 {
     // estimate.py:271,280,290,299
     const double lb[3] = {2., 0.0001, 0.0001};
@@ -505,6 +508,7 @@ __device__ __forceinline__ int trf_minimize(const Eval &evaluate, int m, double 
             cur = trial;
         }
     }
+    nfev_out = nfev;
     return status;
 }
 
@@ -512,7 +516,7 @@ __device__ __forceinline__ int trf_minimize(const Eval &evaluate, int m, double 
 // absolute_sigma=True), reduced chi-square (estimate.py:286-287) and the output maps of one cell.
 template <int NP>
 __device__ __forceinline__ void write_cell(const FitArgs &a, size_t dst, int m, const double (&x)[NP],
-                                           const Normal<NP> &cur, int status)
+                                           const Normal<NP> &cur, int status, int nfev)
 {
     double Bc[NP][NP], lam[NP], V[NP][NP], sd[NP];
 #pragma unroll
@@ -541,7 +545,8 @@ __device__ __forceinline__ void write_cell(const FitArgs &a, size_t dst, int m, 
         a.o_a_std[dst] = sd[NP - 1];
     }
     a.o_chi2[dst] = 2. * cur.cost / (double)(m - NP);
-    if (a.status) a.status[dst] = (status > 0) ? 1 : ((status == -3) ? 3 : 2);
+    // low byte: 1 converged, 2 iteration limit, 3 bad data; upper bits: model evaluations used (SciPy's nfev)
+    if (a.status) a.status[dst] = ((status > 0) ? 1 : ((status == -3) ? 3 : 2)) | (nfev << 8);
 }
 
 __device__ __forceinline__ void write_bad_cell(const FitArgs &a, size_t dst, bool with_alpha)
@@ -720,8 +725,287 @@ __global__ void __launch_bounds__(FIT_NT, CACHE ? 2 : FIT_MIN_BLOCKS) fit_cell_k
         };
         double x[NP];
         Normal<NP> cur;
-        const int status = trf_minimize<NP>(evaluate, m, x, cur);
-        write_cell<NP>(a, dst, m, x, cur, status);
+        int nfev = 0;
+        const int status = trf_minimize<NP>(evaluate, m, x, cur, nfev);
+        write_cell<NP>(a, dst, m, x, cur, status, nfev);
+    }
+}
+
+// ---- lane-persistent fit kernel (default) --------------------------------------------------------
+// The number of model evaluations differs a lot between cells (mean 10, maximum several hundred at the
+// BASELINE sizes).  With one cell per thread per loop trip a warp advances at the pace of its slowest lane
+// and the grid at the pace of its unluckiest thread.  Here every lane keeps its own optimiser state and the
+// loop body is ONE trust-region trial (scaling, eigen-decomposition, step, model evaluation, radius update) of
+// whatever cell the lane currently holds; a lane whose cell has terminated writes it out and takes the next
+// cell from a global counter (one atomic per warp and trip).  The arithmetic of a cell is the sequence of
+// trf_minimize exactly -- the outer-iteration quantities are recomputed from (x, J^T J, J^T r) on a retry
+// instead of being kept, which gives the same values -- so results do not depend on the schedule.
+template <int NP>
+__global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
+{
+    extern __shared__ double fsh[];
+    const bool freeair = a.conf.boug != 1;
+    const bool two = freeair && a.zc_map != nullptr;  // both attenuation terms stored
+    const bool shared_zc = freeair && !two;           // e^{-k wd} stored
+    double *k4 = fsh;                              // [ns] k^4 * Em*1e9/12/(1-nu^2)
+    double *ezc = fsh + a.ns;                      // [ns] e^{-k zc}  (uniform zc)
+    double *sdeep = fsh + 2 * a.ns;                // [ns][FIT_NT]
+    double *stop = sdeep + (size_t)a.ns * FIT_NT;  // [ns][FIT_NT]  (zc grid and free air only, else absent)
+    double *sobs = stop + (two ? (size_t)a.ns * FIT_NT : 0);  // [4][ns][FIT_NT] = adm, 1/eadm, coh, 1/ecoh
+    for (int s = threadIdx.x; s < a.ns; s += FIT_NT) {
+        const double k2 = a.k[s] * a.k[s];
+        k4[s] = (k2 * k2) * (FLEX_EM * 1.e9 / 12. / (1. - FLEX_NU * FLEX_NU));
+        ezc[s] = exp(-a.k[s] * a.conf.zc);
+    }
+    __syncthreads();
+    const long long ncells = (long long)a.fx * a.fy;
+    const size_t nxy = (size_t)a.nx * a.ny;
+    const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
+    const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    // estimate.py:271,280,290,299
+    const double lb3[3] = {2., 0.0001, 0.0001}, ub3[3] = {250., 0.9999, FLEX_PI - 0.001};
+    const double x03[3] = {20., 0.5, FLEX_PI / 2.};
+    double lbp[NP], ubp[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        lbp[p] = lb3[p];
+        ubp[p] = ub3[p];
+    }
+
+    // ---- per-lane state of the cell in flight
+    bool have = false, more = true, init = false;
+    size_t dst = 0;
+    FlexCell fc = flex_cell(a.conf, a.conf.rhoc, a.conf.zc, 0.);
+    double cdeep = 0., ctop = 0.;
+    double x[NP];
+    Normal<NP> cur;
+    double Delta = 0., alpha = 0.;
+    int nfev = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) x[p] = x03[p];
+
+    auto evaluate = [&](const double(&xe)[NP], Normal<NP> &nm) {
+        const double te = xe[0], F = xe[1];
+        const double al = (NP == 3) ? xe[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
+        double sa, ca;
+        sincos(al, &sa, &ca);
+        const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+        double acc[1 + NP + NP * (NP + 1) / 2];
+#pragma unroll
+        for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
+#pragma unroll 2
+        for (int s = 0; s < a.ns; s++) {
+            FlexK fk;
+            fk.k4d = k4[s];
+            fk.deep = sdeep[s * FIT_NT + tid];
+            fk.top = 0.;
+            if (freeair) {
+                if (two) {
+                    fk.top = stop[s * FIT_NT + tid];
+                } else {
+                    fk.top = ctop * fk.deep;
+                    fk.deep = cdeep * (ezc[s] * fk.deep);
+                }
+            }
+            double adm, coh, dA[3], dC[3];
+            flex_eval<true>(fc, fk, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+            if (use_adm) {
+                const double w = sobs[(1 * a.ns + s) * FIT_NT + tid];  // curve_fit: transform = 1/sigma
+                const double r = (adm - sobs[(0 * a.ns + s) * FIT_NT + tid]) * w;
+                double jr[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++) jr[p] = dA[p] * w;
+                accumulate<NP>(acc, r, jr);
+            }
+            if (use_coh) {
+                const double w = sobs[(3 * a.ns + s) * FIT_NT + tid];
+                const double r = (coh - sobs[(2 * a.ns + s) * FIT_NT + tid]) * w;
+                double jr[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++) jr[p] = dC[p] * w;
+                accumulate<NP>(acc, r, jr);
+            }
+        }
+        unpack<NP>(acc, nm);
+    };
+
+    for (;;) {
+        // ---- lanes without a cell take the next one (warp-aggregated atomic: consecutive cells for the lanes
+        // that fetch together, so their loads share sectors)
+        // (a fetch stalls the whole warp for the latency of ~4 ns loads, so idle lanes wait for company unless
+        // nothing else is running in the warp)
+        const unsigned want = __ballot_sync(0xffffffffu, !have && more), busy = __ballot_sync(0xffffffffu, have);
+        if (!have && more && (__popc(want) >= a.fetch_min || busy == 0u)) {
+            const unsigned need = __activemask();
+            const int leader = __ffs(need) - 1, rank = __popc(need & ((1u << lane) - 1u));
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(need, base, leader);
+            const long long cell = (long long)base + rank;
+            if (cell >= ncells) {
+                more = false;
+            } else {
+                const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
+                const size_t src = (size_t)((a.cj0 + cj) * a.nn - a.row0) * a.nx + (size_t)ci * a.nn;
+                dst = (size_t)cj * a.mx + ci;
+                if (!(a.mask && a.mask[src])) {  // classes.py:1228-1231 (outputs of masked cells stay zero)
+                    const double rhoc = a.rhoc_map ? a.rhoc_map[src] : a.conf.rhoc;  // classes.py:1087-1091
+                    const double zc = a.zc_map ? a.zc_map[src] : a.conf.zc;
+                    fc = flex_cell(a.conf, rhoc, zc, a.wd[src]);
+                    cdeep = 2. * FLEX_PI * FLEX_GC * fc.drho;
+                    ctop = 2. * FLEX_PI * FLEX_GC * (fc.A * fc.rcf);
+                    bool bad = false;
+                    for (int s = 0; s < a.ns; s++) {
+                        if (shared_zc) {
+                            sdeep[s * FIT_NT + tid] = (fc.wd == 0.) ? 1. : exp(-a.k[s] * fc.wd);
+                        } else {
+                            const FlexK q = flex_k(fc, a.k[s]);
+                            sdeep[s * FIT_NT + tid] = q.deep;
+                            if (two) stop[s * FIT_NT + tid] = q.top;
+                        }
+                        const size_t o = src + nxy * s;
+                        if (use_adm) {
+                            const double y = __ldg(a.adm + o), e = __ldg(a.eadm + o);
+                            bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                            sobs[(0 * a.ns + s) * FIT_NT + tid] = y;
+                            sobs[(1 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                        }
+                        if (use_coh) {
+                            const double y = __ldg(a.coh + o), e = __ldg(a.ecoh + o);
+                            bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
+                            sobs[(2 * a.ns + s) * FIT_NT + tid] = y;
+                            sobs[(3 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                        }
+                    }
+                    if (bad) {  // SciPy raises ValueError here; we flag the cell
+                        write_bad_cell(a, dst, NP == 3);
+                    } else {
+                        have = true;
+                        init = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have || more)) break;
+
+        // ---- one trust-region trial of the lane's cell (trf_minimize, flattened)
+        bool act = have;
+        double xn[NP], step[NP], step_h[NP], predicted = 0.;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            xn[p] = x03[p];  // the starting point when the cell is new
+            step[p] = step_h[p] = 0.;
+        }
+        if (act && !init) {
+            double v[NP], dv[NP];
+            cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+            double g_norm = 0.;
+#pragma unroll
+            for (int p = 0; p < NP; p++) g_norm = fmax(g_norm, fabs(cur.g[p] * v[p]));
+            int status = -1;
+            if (g_norm < TRF_GTOL) status = 1;
+            if (status != -1 || nfev >= TRF_MAX_NFEV) {
+                write_cell<NP>(a, dst, m, x, cur, status, nfev);
+                have = false;
+                act = false;
+            } else {
+                double d[NP], diag_h[NP], g_h[NP], Bh[NP][NP], Bw[NP][NP], lam[NP], V[NP][NP], suf[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    d[p] = sqrt(v[p]);
+                    diag_h[p] = cur.g[p] * dv[p];
+                    g_h[p] = d[p] * cur.g[p];
+                }
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+#pragma unroll
+                    for (int q = 0; q < NP; q++) {
+                        Bh[p][q] = d[p] * d[q] * cur.B[p][q] + ((p == q) ? diag_h[p] : 0.);
+                        Bw[p][q] = Bh[p][q];
+                    }
+                jacobi_eig<NP>(Bw, lam, V);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {
+                    double sacc = 0.;
+#pragma unroll
+                    for (int q = 0; q < NP; q++) sacc += V[q][p] * g_h[q];
+                    suf[p] = sacc;
+                }
+                const double theta = fmax(0.995, 1. - g_norm);
+                double p_h[NP], pp[NP];
+                solve_tr<NP>(m, lam, V, suf, Delta, alpha, p_h);
+#pragma unroll
+                for (int p = 0; p < NP; p++) pp[p] = d[p] * p_h[p];
+                select_step<NP>(x, Bh, g_h, pp, p_h, d, Delta, lbp, ubp, theta, step, step_h, predicted);
+#pragma unroll
+                for (int p = 0; p < NP; p++) {  // make_strictly_feasible(x + step, rstep=0)
+                    double t = x[p] + step[p];
+                    if (t <= lbp[p]) t = nextafter(lbp[p], ubp[p]);
+                    else if (t >= ubp[p]) t = nextafter(ubp[p], lbp[p]);
+                    xn[p] = t;
+                }
+            }
+        }
+        Normal<NP> trial;
+        if (act) evaluate(xn, trial);
+        if (act) {
+            if (init) {
+                init = false;
+#pragma unroll
+                for (int p = 0; p < NP; p++) x[p] = x03[p];
+                cur = trial;
+                nfev = 1;
+                alpha = 0.;
+                double v[NP], dv[NP], t[NP];
+                cl_scaling<NP>(x, cur.g, lbp, ubp, v, dv);
+#pragma unroll
+                for (int p = 0; p < NP; p++) t[p] = x[p] / sqrt(v[p]);
+                Delta = vnorm<NP>(t);
+                if (Delta == 0.) Delta = 1.;
+                if (!isfinite(cur.cost)) {  // "Residuals are not finite in the initial point"
+                    write_cell<NP>(a, dst, m, x, cur, -3, nfev);
+                    have = false;
+                }
+            } else {
+                nfev++;
+                const double step_h_norm = vnorm<NP>(step_h);
+                if (!isfinite(trial.cost)) {
+                    Delta = 0.25 * step_h_norm;
+                } else {
+                    const double actual = cur.cost - trial.cost;
+                    // update_tr_radius
+                    double ratio, Delta_new = Delta;
+                    if (predicted > 0.) ratio = actual / predicted;
+                    else if (predicted == 0. && actual == 0.) ratio = 1.;
+                    else ratio = 0.;
+                    if (ratio < 0.25) Delta_new = 0.25 * step_h_norm;
+                    else if (ratio > 0.75 && step_h_norm > 0.95 * Delta) Delta_new = 2.0 * Delta;
+                    const double step_norm = vnorm<NP>(step);
+                    // check_termination
+                    const bool f_ok = (actual < TRF_FTOL * cur.cost) && (ratio > 0.25);
+                    const bool x_ok = step_norm < TRF_XTOL * (TRF_XTOL + vnorm<NP>(x));
+                    int status = -1;
+                    if (f_ok && x_ok) status = 4;
+                    else if (f_ok) status = 2;
+                    else if (x_ok) status = 3;
+                    if (status == -1) {
+                        alpha *= Delta / Delta_new;
+                        Delta = Delta_new;
+                    }
+                    if (actual > 0.) {
+#pragma unroll
+                        for (int p = 0; p < NP; p++) x[p] = xn[p];
+                        cur = trial;
+                    }
+                    if (status != -1) {
+                        write_cell<NP>(a, dst, m, x, cur, status, nfev);
+                        have = false;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -850,9 +1134,10 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
 
         double x[NP];
         Normal<NP> cur;
-        const int status = trf_minimize<NP>(evaluate, m, x, cur);
+        int nfev = 0;
+        const int status = trf_minimize<NP>(evaluate, m, x, cur, nfev);
 
-        if (lane == 0) write_cell<NP>(a, dst, m, x, cur, status);
+        if (lane == 0) write_cell<NP>(a, dst, m, x, cur, status, nfev);
     }
 }
 
@@ -916,10 +1201,18 @@ int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
         kernel<<<(unsigned)blocks, FIT_NT, smem, stream>>>(a);
         return PFX_OK;
     };
-    if (alph)
+    // default: the lane-persistent kernel (needs the shared-memory cache and a work counter)
+    const char *me = getenv("PLATEFLEX_B200_FIT");
+    const bool lanes = cache && a.counter && !(me && !strcmp(me, "static"));
+    if (lanes) {
+        const int resident = 2 * nsm;  // two CTAs per SM, each lane pulls cells until the counter runs out
+        if (blocks > resident) blocks = resident;
+        PFX_CHECK(alph ? launch(fit_lane_kernel<3>) : launch(fit_lane_kernel<2>));
+    } else if (alph) {
         PFX_CHECK(cache ? launch(fit_cell_kernel<3, true>) : launch(fit_cell_kernel<3, false>));
-    else
+    } else {
         PFX_CHECK(cache ? launch(fit_cell_kernel<2, true>) : launch(fit_cell_kernel<2, false>));
+    }
     PFX_CUDA(cudaGetLastError());
     return PFX_OK;
 }
@@ -929,6 +1222,29 @@ int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 }  // namespace pfx
 
 using namespace pfx;
+
+// Work counters of the lane-persistent fit kernel: a small per-device ring of device words, one per
+// launch, zeroed on the launch stream.  A word comes round again after FIT_COUNTERS launches.
+namespace {
+constexpr int FIT_COUNTERS = 64, FIT_MAX_DEVICES = 64;
+std::mutex g_counter_mutex;
+unsigned long long *g_counters[FIT_MAX_DEVICES] = {};
+unsigned g_counter_next[FIT_MAX_DEVICES] = {};
+
+unsigned long long *next_fit_counter(int device)
+{
+    if (device < 0 || device >= FIT_MAX_DEVICES) return nullptr;
+    std::lock_guard<std::mutex> lock(g_counter_mutex);
+    if (!g_counters[device]) {
+        if (cudaMalloc(&g_counters[device], FIT_COUNTERS * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            g_counters[device] = nullptr;
+            return nullptr;
+        }
+    }
+    return g_counters[device] + (g_counter_next[device]++ % FIT_COUNTERS);
+}
+}  // namespace
 
 extern "C" {
 
@@ -1010,6 +1326,11 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
     a.o_a_std = out_alpha_std;
     a.o_chi2 = out_chi2;
     a.status = status;
+    a.counter = next_fit_counter(device);
+    {
+        const char *fb = getenv("PLATEFLEX_B200_FIT_BATCH");
+        a.fetch_min = (fb && atoi(fb) >= 1 && atoi(fb) <= 32) ? atoi(fb) : 24;
+    }
     const size_t mo = (size_t)a.mx * a.my;
     int rc = PFX_OK;
     auto zero = [&](void *p, size_t bytes) {
@@ -1028,6 +1349,7 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
         zero(out_alpha_std, mo * 8);
     }
     zero(status, mo * 4);
+    zero(a.counter, sizeof(unsigned long long));
     if (rc == PFX_OK && a.fx > 0 && a.fy > 0) {
         // range(0, nx-nn, nn) never reaches index mx*nn or beyond (classes.py:1218 vs 1189)
         int nsm = 148;

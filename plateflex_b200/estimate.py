@@ -32,7 +32,7 @@ def L2_estimate_grid(k, wl_admit, ewl_admit, wl_coh, ewl_coh, wd, rhoc=None, zc=
                      atype="joint", device=None, strict=False):
     """Fit all cells ``(i, j)`` with i in range(0, nx-nn, nn), j in range(0, ny-nn, nn)
     (classes.py:1218-1219).  Inputs are (nx, ny, ns) maps and (nx, ny) grids; returns a dict of
-    (nx//nn, ny//nn) maps: mean_Te, std_Te, mean_F, std_F, chi2[, mean_a, std_a], status.
+    (nx//nn, ny//nn) maps: mean_Te, std_Te, mean_F, std_F, chi2[, mean_a, std_a], status, nfev.
 
     ``strict=True`` raises like SciPy would for the first cell that did not converge
     (RuntimeError) or holds unusable data (ValueError); otherwise such cells are flagged
@@ -65,8 +65,9 @@ def L2_estimate_grid(k, wl_admit, ewl_admit, wl_coh, ewl_coh, wd, rhoc=None, zc=
         dev, C.byref(conf), _lib.ptr(k), ns, nx, ny, *[_lib.ptr(m) for m in maps], _lib.ptr(wd_a), _lib.ptr(rhoc_a),
         _lib.ptr(zc_a), _lib.ptr(mask_a), int(nn), int(alph), _lib.ATYPES[atype],
         *[_lib.ptr(out.get(n)) for n in names], _lib.ptr(status)))
-    out["status"] = status
-    _report(status, strict)
+    out["status"] = status & 0xff
+    out["nfev"] = status >> 8  # model evaluations per cell (least_squares' nfev)
+    _report(out["status"], strict)
     return out
 
 

@@ -389,6 +389,9 @@ def test_row_sharded_fit_equals_full_grid_fit(pf, nn, world, alph):
         for n in names:
             pieces[n].append(o[idx[n]][:mx * myl.value].cpu().numpy().reshape(myl.value, mx))
         pieces["status"].append(st[:mx * myl.value].cpu().numpy().reshape(myl.value, mx))
+    raw = np.concatenate(pieces["status"], axis=0).T
+    assert np.array_equal(raw >> 8, full["nfev"]) and (full["nfev"][full["status"] == 1] >= 2).all()
+    pieces["status"] = [p & 0xff for p in pieces["status"]]
     for n in names + ["status"]:
         got = np.concatenate(pieces[n], axis=0).T  # (mx, my)
         assert got.shape == full[n].shape, (n, got.shape, full[n].shape)
