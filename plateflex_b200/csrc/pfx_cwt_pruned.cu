@@ -457,7 +457,7 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
             // every transform has the same number of rows: one wave of persistent CTAs when a line is a single
             // part; with several parts per line (N > 2048, two CTAs per SM) 192 CTAs per transform measured 7 %
             // faster than one wave (the rows of a CTA stay closer together, the tail is finer)
-            const bool multi = (st->v2x[is] >> 6) & 1;
+            const bool multi = (st->v2x[is] >> 5) & 1;
             const int ctas = ctas_env ? st->ctas_per_transform : (multi ? 192 : std::max(1, st->v2x_ctas[is] / ntr));
             PFX_CHECK(v2_launch_p2(va, sd.ax.logL, st->v2x[is], dim3(std::min(groups, ctas), ntr), pl->stream));
         } else {

@@ -16,7 +16,7 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 # one timed step = 60 pass/reduce launches after 3 warm-up steps; then the fit launches
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"pass|reduce|fit_cell" -s 180 -c 64 --csv --log-file gpurun_out/traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
-for ks in reduce_kernel:77:3 pass2_kernel:77:3 pass1_kernel:77:3 fit_cell_kernel:1:1; do
+for ks in reduce_kernel:77:3 pass2_kernel:77:3 pass1_kernel:77:3 fit_:1:1; do
   k=${ks%%:*}; r=${ks#*:}; s=${r%%:*}; c=${r#*:}
   ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c $c -o gpurun_out/full_$k -f $CMD > gpurun_out/ncu_$k.log 2>&1
 done
