@@ -10,14 +10,18 @@
 // max_nfev=1000), an un-vendored dependency; its published algorithm
 // (Branch, Coleman & Li 1999; More 1977 for the trust-region sub-problem) is
 // restated here for n<=3 parameters.  With n<=3 everything the method needs
-// from the Jacobian is the n x n matrix J^T J and the gradient J^T f, which a
-// group of G lanes accumulates over the wavelet-scale axis with shuffles; the
-// SVD of the (augmented, Coleman-Li scaled) Jacobian becomes a Jacobi
-// eigen-decomposition of an n x n matrix.  The Jacobian is analytic
-// (pfx_flex.cuh) where SciPy uses 2-point finite differences.
+// from the Jacobian is the n x n matrix J^T J and the gradient J^T f,
+// accumulated over the wavelet-scale axis; the SVD of the (augmented,
+// Coleman-Li scaled) Jacobian becomes a Jacobi eigen-decomposition of an n x n
+// matrix.  The Jacobian is analytic (pfx_flex.cuh) where SciPy uses 2-point
+// finite differences.
 //
-// One group of G lanes per grid cell, scales strided over the lanes; all lanes
-// of a group carry identical copies of the small dense algebra.
+// Three kernels share the optimiser:
+//   fit_lane_kernel  (default) one lane per cell in flight, one trust-region trial per loop
+//                    trip, cells handed out by a global counter
+//   fit_cell_kernel  (PLATEFLEX_B200_FIT=static) one cell per thread per grid-stride trip;
+//                    also the fallback when the shared-memory cache does not fit
+//   fit_kernel       (PLATEFLEX_B200_FIT=group) G lanes per cell, scales strided over the lanes
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
