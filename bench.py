@@ -116,8 +116,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
         self.i0, self.i1 = 0, None
 
     def mark_start(self):
@@ -128,6 +128,8 @@ class ClockSampler:
         self.i1 = len(self.rows)
 
     def __enter__(self):
+        if not self.enabled:  # only the rank that prints the JSON line polls nvidia-smi
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -296,7 +298,7 @@ def main():
         torch.cuda.synchronize()
 
     times = []
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         for _ in range(args.warmup):
             step_dev()
         barrier()
