@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "pfx_plan.hpp"
 
@@ -368,6 +369,16 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     if (pruned) PFX_CHECK(pruned_prepare(pl, ngrids));
     // With two plane buffers (pruned engine) the reduction of scale s overlaps the passes of scale s+1.
     const int nbuf = pruned ? pruned_num_buffers(pl) : 1;
+    // Pageable host destinations (plain numpy arrays): every scale is enqueued first, then the finished
+    // scales are drained through the pinned staging chunks of pfx_hostio.cu while the later ones compute.
+    const bool staged = (h32 && host_is_pageable(h32[0])) || (!h32 && h_outs && host_is_pageable(h_outs[0]));
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events()
+        {
+            for (cudaEvent_t e : v) cudaEventDestroy(e);
+        }
+    } scale_done;
     // (per-kernel timing serialises everything on the caller's stream so that event pairs time one kernel each)
     const bool overlap = nbuf == 2 && mode != OUT_CUBE && !pl->profiling;
     cudaStream_t red_stream = overlap ? pl->s_aux : pl->stream;
@@ -410,7 +421,12 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         }
         pl->launches++;
         if (overlap || h_outs || h32) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));
-        if (h32) {
+        if (staged) {
+            cudaEvent_t e = nullptr;
+            PFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            scale_done.v.push_back(e);
+            PFX_CUDA(cudaEventRecord(e, red_stream));
+        } else if (h32) {
             PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_reduced[b], 0));
             for (int i = 0; i < nouts; i++)
                 PFX_CUDA(cudaMemcpyAsync(h32[i] + so * elems[i], d32[i] + so * elems[i],
@@ -426,6 +442,20 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     if (overlap) {
         PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_aux));
         PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
+    }
+    if (staged) {
+        for (int is = is0; is < is1; is++) {
+            const size_t so = (size_t)(is - is0) * nxy;
+            PFX_CUDA(cudaEventSynchronize(scale_done.v[is - is0]));
+            for (int i = 0; i < nouts; i++) {
+                if (h32)
+                    PFX_CHECK(staged_d2h(h32[i] + so * elems[i], d32[i] + so * elems[i], nxy * elems[i] * sizeof(float),
+                                         pl->s_copy));
+                else
+                    PFX_CHECK(staged_d2h(h_outs[i] + so * elems[i], d_outs[i] + so * elems[i],
+                                         nxy * elems[i] * sizeof(double), pl->s_copy));
+            }
+        }
     }
     if (h_outs || h32) {
         PFX_CUDA(cudaEventRecord(pl->ev_join, pl->s_copy));
@@ -518,8 +548,8 @@ static int transform_to_host(pfx_plan *pl, const double *grid, int is0, int is1,
             PFX_CHECK(enqueue(is + 1, b ^ 1));
         }
         PFX_CUDA(cudaStreamWaitEvent(pl->s_copy, pl->ev_planes[b], 0));
-        PFX_CUDA(cudaMemcpyAsync(static_cast<char *>(cube) + (size_t)(is - is0) * slab_bytes, d_slab[b], slab_bytes,
-                                 cudaMemcpyDeviceToHost, pl->s_copy));
+        // (pageable cube: staged through pinned chunks, a thread team takes the first-touch faults)
+        PFX_CHECK(staged_d2h(static_cast<char *>(cube) + (size_t)(is - is0) * slab_bytes, d_slab[b], slab_bytes, pl->s_copy));
         PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], pl->s_copy));
     }
     PFX_CUDA(cudaStreamSynchronize(pl->s_copy));

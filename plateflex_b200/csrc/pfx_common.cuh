@@ -86,6 +86,11 @@ struct ShardOut {
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
                   double *out3, cudaStream_t stream, const ShardOut *shards = nullptr, bool f32 = false);
 
+// Copies between the device and pageable host memory through pinned chunks and a thread team (pfx_hostio.cu)
+bool host_is_pageable(const void *p);
+int staged_d2h(void *dst, const void *src_dev, size_t bytes, cudaStream_t st);
+int staged_h2d(void *dst_dev, const void *src, size_t bytes, cudaStream_t st);
+
 // K4: copy 11 planes of a view into a compact (nx, ny, 11) cube slab of double2, or float2 with c64.
 int launch_crop(int nx, int ny, PlaneView w, void *slab, bool c64, cudaStream_t stream);
 

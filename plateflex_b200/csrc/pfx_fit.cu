@@ -1404,10 +1404,7 @@ int pfx_l2_fit_host(int device, const pfx_flex_conf *conf, const double *k, int 
             return nullptr;
         }
         bufs.push_back(d);
-        if (cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) {
-            set_error("H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = PFX_ERR_CUDA;
-        }
+        if (staged_h2d(d, h, bytes, 0) != PFX_OK) rc = PFX_ERR_CUDA;  // pageable numpy maps: pinned chunks + thread team
         return d;
     };
     auto dn = [&](void *h, size_t bytes) -> void * {
