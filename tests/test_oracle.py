@@ -159,3 +159,64 @@ def test_oracle_matches_golden_fixtures(ora):
         conf = ora.FlexConf(wd=float(f["wd"][c]), boug=int(f["boug"]), rhoc=float(f["rhoc"]), zc=float(f["zc"]))
         a, co = ora.real_xspec_functions(f["k"], f["te"][c], f["f"][c], f["alpha"][c], conf)
         assert np.allclose(a, f["admit"][c], rtol=1e-13) and np.allclose(co, f["coh"][c], rtol=1e-13)
+
+
+# ---- property tests (hypothesis): the oracle against the algebra of the reference's formulas -------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=12, deadline=None)
+@given(nx=st.integers(3, 24), ny=st.integers(3, 24), seed=st.integers(0, 10_000), a=st.floats(-3.0, 3.0),
+       b=st.floats(-3.0, 3.0))
+def test_transform_is_linear_and_blind_to_the_mean(ora, nx, ny, seed, a, b):
+    # cpwt.f90:110-111 removes the mean before the FFT; everything after is linear in the grid
+    rng = np.random.default_rng(seed)
+    g1, g2 = rng.standard_normal((nx, ny)), rng.standard_normal((nx, ny))
+    kf = np.array([3e-5, 1.1e-4])
+    w1, w2 = ora.wlet_transform(g1, 9.0, 11.0, kf), ora.wlet_transform(g2, 9.0, 11.0, kf)
+    wc = ora.wlet_transform(a * g1 + b * g2 + 123.0, 9.0, 11.0, kf)
+    scale = max(np.abs(w1).max() * abs(a), np.abs(w2).max() * abs(b), 1e-300)
+    assert np.abs(wc - (a * w1 + b * w2)).max() <= 1e-11 * scale + 1e-13
+
+
+@settings(max_examples=10, deadline=None)
+@given(seed=st.integers(0, 10_000), c=st.floats(0.01, 50.0))
+def test_admittance_of_a_scaled_copy_is_the_scale_factor(ora, seed, c):
+    # cpwt.f90:330-355: with grid 2 = c * grid 1, xsg = c*sg1 and sg2 = c^2*sg1 at every azimuth, so admittance = c,
+    # coherence = 1 and every prefix ratio of the jackknife (cpwt_sub.f90:329-335) is the same: zero spread
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((12, 10))
+    kf = np.array([4e-5, 9e-5])
+    w = ora.wlet_transform(g, 10.0, 10.0, kf)
+    adm, eadm, coh, ecoh = ora.wlet_admit_coh(w, c * w)
+    assert np.allclose(adm, c, rtol=1e-12) and np.allclose(coh, 1.0, rtol=1e-12)
+    assert np.abs(eadm).max() <= 1e-12 * c and np.abs(ecoh).max() <= 1e-12
+
+
+@settings(max_examples=20, deadline=None)
+@given(te=st.floats(2.0, 250.0), f=st.floats(0.001, 0.99), alpha=st.floats(0.01, 3.1), wd=st.floats(0.0, 6000.0),
+       boug=st.integers(0, 1))
+def test_flex_model_against_the_formulas_of_flex_f90(ora, te, f, alpha, wd, boug):
+    # SURVEY.md appendix A8 / flex.f90:199-231 written out with numpy; rhof follows the water depth
+    k = np.geomspace(3e-6, 2e-4, 9)
+    conf = ora.FlexConf(wd=wd, boug=boug, rhoc=2750.0, zc=33.0e3)
+    adm, coh = ora.real_xspec_functions(k, te, f, alpha, conf)
+    g, em, nu, gc = 9.81, 1.0e11, 0.25, 6.67e-6
+    rhom, rhoc, rhof = 3200.0, 2750.0, (1030.0 if wd > 0 else 0.0)
+    A = 0.0 if boug == 1 else 1.0
+    drho, rcf = rhom - rhoc, rhoc - rhof
+    psi = em * (te * 1.0e3) ** 3 / 12.0 / (1.0 - nu ** 2) * k ** 4
+    r = rcf / drho
+    theta = -r / (1.0 + psi / drho / g)
+    phi = -r * (1.0 + psi / rcf / g)
+    mu_h, mu_w = 1.0 / (1.0 - theta), 1.0 / (phi - 1.0)
+    top, deep = A * rcf * np.exp(-k * wd), drho * np.exp(-k * (33.0e3 + wd))
+    nu_h = 2 * np.pi * gc * (top + deep * theta) / (1.0 - theta)
+    nu_w = 2 * np.pi * gc * (top + deep * phi) / (phi - 1.0)
+    ff = f / (1.0 - f) * r
+    ea = np.exp(1j * alpha)
+    hg = nu_h * mu_h + nu_w * mu_w * ff ** 2 + (nu_h * mu_w * ea + nu_w * mu_h * np.conj(ea)) * ff
+    hh = mu_h ** 2 + (mu_w * ff) ** 2 + 2 * mu_h * mu_w * ff * np.cos(alpha)
+    gg = nu_h ** 2 + (nu_w * ff) ** 2 + 2 * nu_h * nu_w * ff * np.cos(alpha)
+    assert np.allclose(adm, np.real(hg) / hh, rtol=1e-10, atol=1e-16)
+    assert np.allclose(coh, np.real(hg / np.sqrt(hh) / np.sqrt(gg)) ** 2, rtol=1e-10, atol=1e-16)
