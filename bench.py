@@ -232,6 +232,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--balance", default="blocks", choices=["blocks", "deal"],
+                    help="strong scaling with --exchange p2p: contiguous cost-balanced scale blocks, or scales dealt "
+                         "out by decreasing cost (longest processing time first)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="strong scaling: epilogue stores into peer row shards over NVLink (p2p) or NCCL all-to-all")
     ap.add_argument("--engine", default=os.environ.get("PLATEFLEX_B200_ENGINE", "pruned"))
@@ -282,9 +285,14 @@ def main():
     resharder = sharding.RowResharder(nx, ny, ns, world, rank, dev, cost=cost) if (strong and not p2p) else None
     peers = sharding.PeerShards(nx, ny, ns, world, rank, local) if p2p else None
 
+    my_scales = sharding.deal_scales(cost, world)[rank] if (p2p and args.balance == "deal") else None
+
     def step_dev():
         if p2p:  # the epilogue of every scale stores its rows straight into the owners' shards (NVLink)
-            peers.transform(plan, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1)
+            if my_scales is not None:
+                peers.transform_scales(plan, d_topo.data_ptr(), d_grav.data_ptr(), my_scales)
+            else:
+                peers.transform(plan, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1)
             return
         if nsl > 0:
             _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, d_topo.data_ptr(), d_grav.data_ptr(), is0, is1,
@@ -503,6 +511,7 @@ def main():
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"], "engine": args.engine, "l2": "flushed between timed steps (256 MiB write)",
                    "cpu_affinity": f"{numa_cpus} CPUs of the GPU's NUMA node" if numa_cpus else "not set",
+                   "balance": args.balance if p2p else None,
                    "sharding": ((f"scales over {world} ranks, epilogue stores into peer row shards over NVLink (CUDA IPC)"
                                  if p2p else f"scales over {world} ranks + NCCL all-to-all to row shards") if strong else
                                 (f"{world} independent grid pairs, one per rank" if world > 1 else "single GPU"))},

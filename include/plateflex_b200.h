@@ -161,6 +161,11 @@ int pfx_wlet_admit_coh_host_f32(pfx_plan *plan, const double *topo, const double
  * before any shard is read. */
 int pfx_wlet_admit_coh_sharded_dev(pfx_plan *plan, const double *topo_dev, const double *grav_dev, int is0, int is1,
                                    int nshards, void *const *shard_bases);
+/* Same for an arbitrary set of scales (nscales indices into the plan's wavenumbers, transformed in the given
+ * order): with the one-sided exchange a rank's scales need not be contiguous, so they can be dealt out by
+ * cost (pfx_plan_scale_cost) instead of cut into blocks. */
+int pfx_wlet_admit_coh_sharded_list_dev(pfx_plan *plan, const double *topo_dev, const double *grav_dev,
+                                        const int *scales, int nscales, int nshards, void *const *shard_bases);
 /* bytes of shard q's buffer: 4 * ns * rows_q * nx * sizeof(double) */
 size_t pfx_shard_bytes(int nx, int ny, int ns, int nshards, int q);
 /* Device memory that other processes on the node can map (cudaMalloc + cudaIpcGetMemHandle /

@@ -69,6 +69,7 @@ _SIGS = {
     "pfx_wlet_scalogram_host_f32": ([_vp, _vp, _i, _i, _vp, _vp], _i),
     "pfx_wlet_admit_coh_host_f32": ([_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_wlet_admit_coh_sharded_dev": ([_vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    "pfx_wlet_admit_coh_sharded_list_dev": ([_vp, _vp, _vp, _vp, _i, _i, _vp], _i),
     "pfx_shard_bytes": ([_i, _i, _i, _i, _i], C.c_size_t),
     "pfx_ipc_alloc": ([_i, C.c_size_t, C.POINTER(_vp), _vp], _i),
     "pfx_ipc_free": ([_i, _vp], _i),

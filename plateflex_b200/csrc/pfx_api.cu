@@ -359,8 +359,11 @@ int check_range(const pfx_plan *pl, int is0, int is1)
 // (each float64 result rounded once) into the device staging arrays d32 and the host receives those.
 int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0, int is1, double *const *d_outs,
             double *const *h_outs, const int *elems, int nouts, const ShardOut *shards = nullptr,
-            float *const *d32 = nullptr, float *const *h32 = nullptr)
+            float *const *d32 = nullptr, float *const *h32 = nullptr, const int *scale_list = nullptr)
 {
+    // scale_list (optional, is1 - is0 entries): the scales to transform, in this order, instead of the
+    // contiguous range [is0, is1) -- a multi-GPU caller may own any subset of the scale axis
+    const int is_base = is0;
     const int ngrids = g2 ? 2 : 1;
     const size_t nxy = (size_t)pl->nx * pl->ny;
     PFX_CHECK(forward_spectrum(pl, g1, 0));
@@ -382,9 +385,10 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     // (per-kernel timing serialises everything on the caller's stream so that event pairs time one kernel each)
     const bool overlap = nbuf == 2 && mode != OUT_CUBE && !pl->profiling;
     cudaStream_t red_stream = overlap ? pl->s_aux : pl->stream;
-    for (int is = is0; is < is1; is++) {
-        const int b = (is - is0) & 1;
-        const size_t so = (size_t)(is - is0) * nxy;
+    for (int n = 0; n < is1 - is_base; n++) {
+        const int is = scale_list ? scale_list[n] : is_base + n;  // n: position in this call's sequence
+        const int b = n & 1;
+        const size_t so = (size_t)n * nxy;
         PlaneView v1, v2;
         if (!pruned) {
             PFX_CHECK(dense_scale_planes(pl, is, ngrids));
@@ -393,7 +397,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         } else {
             if (overlap) {
                 pruned_select_buffer(pl, b);
-                if (is - is0 >= 2) PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_reduced[b], 0));
+                if (n >= 2) PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_reduced[b], 0));
             }
             PFX_CHECK(pruned_scale_planes(pl, is, ngrids));
             v1 = pruned_view(pl, 0);
@@ -444,9 +448,9 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_join, 0));
     }
     if (staged) {
-        for (int is = is0; is < is1; is++) {
-            const size_t so = (size_t)(is - is0) * nxy;
-            PFX_CUDA(cudaEventSynchronize(scale_done.v[is - is0]));
+        for (int n = 0; n < is1 - is_base; n++) {
+            const size_t so = (size_t)n * nxy;
+            PFX_CUDA(cudaEventSynchronize(scale_done.v[n]));
             for (int i = 0; i < nouts; i++) {
                 if (h32)
                     PFX_CHECK(staged_d2h(h32[i] + so * elems[i], d32[i] + so * elems[i], nxy * elems[i] * sizeof(float),
@@ -671,6 +675,27 @@ int pfx_wlet_admit_coh_sharded_dev(pfx_plan *pl, const double *topo, const doubl
     DeviceGuard guard(pl->device);
     const int el[4] = {1, 1, 1, 1};
     return run_cwt(pl, RED_ADMIT_COH, topo, grav, is0, is1, nullptr, nullptr, el, 4, &sh);
+}
+
+int pfx_wlet_admit_coh_sharded_list_dev(pfx_plan *pl, const double *topo, const double *grav, const int *scales,
+                                        int nscales, int nshards, void *const *shard_bases)
+{
+    PFX_ARG(pl && topo && grav && scales && shard_bases, "null pointer");
+    PFX_ARG(nscales >= 1 && nscales <= pl->ns, "nscales out of range");
+    PFX_ARG(nshards >= 1 && nshards <= PFX_MAX_SHARDS, "nshards must be in [1, PFX_MAX_SHARDS]");
+    for (int n = 0; n < nscales; n++) PFX_ARG(scales[n] >= 0 && scales[n] < pl->ns, "scale index out of range");
+    ShardOut sh;
+    sh.nshards = nshards;
+    sh.rows_per_shard = (pl->ny + nshards - 1) / nshards;
+    sh.ns = pl->ns;
+    for (int q = 0; q < nshards; q++) {
+        const bool has_rows = q * sh.rows_per_shard < pl->ny;
+        PFX_ARG(shard_bases[q] || !has_rows, "null shard buffer");
+        sh.base[q] = reinterpret_cast<double *>(shard_bases[q]);
+    }
+    DeviceGuard guard(pl->device);
+    const int el[4] = {1, 1, 1, 1};
+    return run_cwt(pl, RED_ADMIT_COH, topo, grav, 0, nscales, nullptr, nullptr, el, 4, &sh, nullptr, nullptr, scales);
 }
 
 size_t pfx_shard_bytes(int nx, int ny, int ns, int nshards, int q)

@@ -16,7 +16,7 @@ CPU tensors with the gloo backend (tests/test_sharding.py) and on CUDA tensors w
 import torch
 import torch.distributed as dist
 
-__all__ = ["scale_range", "balanced_cuts", "row_range", "rows_per_shard", "RowResharder", "PeerShards", "gather_rows"]
+__all__ = ["scale_range", "balanced_cuts", "deal_scales", "row_range", "rows_per_shard", "RowResharder", "PeerShards", "gather_rows"]
 
 
 def scale_range(ns, world, rank, cost=None):
@@ -52,6 +52,20 @@ def balanced_cuts(cost, parts):
     for p in range(parts, 0, -1):
         cuts.append(arg[p][cuts[-1]])
     return cuts[::-1]
+
+
+def deal_scales(cost, world):
+    """Longest-processing-time assignment of scales to ranks: scales sorted by decreasing cost, each given
+    to the least loaded rank.  Returns one ascending list of scale indices per rank.  Only the one-sided
+    exchange (PeerShards) can use it: its epilogue stores every scale at its own index."""
+    order = sorted(range(len(cost)), key=lambda s: (-float(cost[s]), s))
+    load = [0.0] * world
+    mine = [[] for _ in range(world)]
+    for s in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        load[r] += float(cost[s])
+        mine[r].append(s)
+    return [sorted(m) for m in mine]
 
 
 def rows_per_shard(ny, world):
@@ -165,6 +179,13 @@ class PeerShards:
         if is1 > is0:
             self._lib.check(self._lib.lib.pfx_wlet_admit_coh_sharded_dev(plan.handle, topo_ptr, grav_ptr, is0, is1,
                                                                          self.world, self.bases))
+
+    def transform_scales(self, plan, topo_ptr, grav_ptr, scales):
+        """Same for an arbitrary list of scale indices (deal_scales)."""
+        if len(scales):
+            arr = (self._C.c_int * len(scales))(*[int(s) for s in scales])
+            self._lib.check(self._lib.lib.pfx_wlet_admit_coh_sharded_list_dev(plan.handle, topo_ptr, grav_ptr, arr,
+                                                                              len(scales), self.world, self.bases))
 
     def local_map_ptrs(self):
         """Device pointers of this rank's four (nx, nrows, ns) maps."""

@@ -471,14 +471,29 @@ def test_sharded_epilogue_writes_the_row_shard_layout(pf, engine, nshards):
         _lib.check(_lib.lib.pfx_wlet_admit_coh_sharded_dev(plan.handle, d_t.data_ptr(), d_g.data_ptr(), is0, is1,
                                                            nshards, bases))
     torch.cuda.synchronize()
-    for q in range(nshards):
-        r0, r1 = sharding.row_range(ny, nshards, q)
-        if r1 == r0:
-            continue
-        got = bufs[q].cpu().numpy()[:4 * ns * (r1 - r0) * nx].reshape(4, ns, r1 - r0, nx)
-        for m in range(4):
-            ref = np.transpose(want[m], (2, 1, 0))[:, r0:r1, :]
-            assert np.array_equal(got[m], ref, equal_nan=True), (q, m)
+
+    def check():
+        for q in range(nshards):
+            r0, r1 = sharding.row_range(ny, nshards, q)
+            if r1 == r0:
+                continue
+            got = bufs[q].cpu().numpy()[:4 * ns * (r1 - r0) * nx].reshape(4, ns, r1 - r0, nx)
+            for m in range(4):
+                ref = np.transpose(want[m], (2, 1, 0))[:, r0:r1, :]
+                assert np.array_equal(got[m], ref, equal_nan=True), (q, m)
+
+    check()
+    # scales dealt out by cost instead of cut into blocks (non-contiguous lists, any order)
+    for b in bufs:
+        b.fill_(float("nan"))
+    dealt = sharding.deal_scales(plan.scale_cost(), 3)
+    assert sorted(s for part in dealt for s in part) == list(range(ns))
+    for part in dealt:
+        arr = (C.c_int * len(part))(*part[::-1])
+        _lib.check(_lib.lib.pfx_wlet_admit_coh_sharded_list_dev(plan.handle, d_t.data_ptr(), d_g.data_ptr(), arr,
+                                                                len(part), nshards, bases))
+    torch.cuda.synchronize()
+    check()
 
 
 def test_float32_outputs_are_the_float64_results_rounded_once(pf, engine):

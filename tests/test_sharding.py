@@ -99,3 +99,17 @@ def test_balanced_cuts_minimise_the_heaviest_block():
     # every rank sees the same cuts; ranges tile the axis
     r = [sharding.scale_range(len(cost), 4, q, cost) for q in range(4)]
     assert r[0][0] == 0 and r[-1][1] == len(cost) and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def test_deal_scales_balances_better_than_blocks():
+    from plateflex_b200 import sharding
+    cost = [2.8, 2.8, 2.9, 3.0, 3.1, 3.3, 3.6, 3.9, 4.1, 4.3, 4.6, 4.9, 5.2, 5.5, 5.8, 6.2, 6.6, 7.0, 7.3, 7.6]
+    world = 8
+    dealt = sharding.deal_scales(cost, world)
+    assert sorted(s for part in dealt for s in part) == list(range(len(cost)))
+    assert all(part == sorted(part) for part in dealt)
+    cuts = sharding.balanced_cuts(cost, world)
+    worst_block = max(sum(cost[a:b]) for a, b in zip(cuts, cuts[1:]))
+    worst_dealt = max(sum(cost[s] for s in part) for part in dealt)
+    assert worst_dealt <= worst_block
+    assert worst_dealt <= 1.15 * sum(cost) / world
