@@ -85,6 +85,22 @@ int pfx_device_count(int *count);
 /* cpwt_sub.f90:26-33 (npow2): smallest power of two >= n, at least 2. */
 int pfx_npow2(int n);
 
+/* Measured FP64 peak of the device: a kernel of independent DFMA chains (8 per thread, all SMs full), timed
+ * with CUDA events; *tflops = 2 * fused multiply-adds / second / 1e12.  The denominator of the FP64 rooflines
+ * bench.py reports (the driver's MEASURED_PEAKS.json holds no FP64 figure). */
+int pfx_fp64_peak(int device, double *tflops);
+
+/* ---- device buffers ---------------------------------------------------- */
+/* For callers that have no device allocator of their own: the Python layer keeps the four (nx,ny,ns)
+ * maps of Project.wlet_admit_coh (classes.py:916-975) on the device so that Project.estimate_grid
+ * (classes.py:1125-1332) fits them in place, and copies a map to the host only when its attribute is
+ * read.  Copies are synchronous; pageable host memory (plain numpy arrays) is staged through pinned
+ * chunks by a small thread team. */
+int pfx_dev_alloc(int device, size_t bytes, void **dev_ptr);
+int pfx_dev_free(int device, void *dev_ptr);
+int pfx_dev_h2d(int device, void *dst_dev, const void *src_host, size_t bytes);
+int pfx_dev_d2h(int device, void *dst_host, const void *src_dev, size_t bytes);
+
 /* ---- CWT plan --------------------------------------------------------- */
 /* Fixes (nx, ny, dx, dy, k[ns], k0) -- the arguments of cpwt.wlet_transform
  * (cpwt.f90:65) other than the data -- allocates device workspaces and builds

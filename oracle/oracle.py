@@ -109,6 +109,19 @@ def wlet_transform(grid, dx, dy, kf, k0=K0_F32, prec=64, nthreads=1):
     return out
 
 
+def wlet_planes(grid, dx, dy, kscale, ia0, ia1, k0=K0_F32, prec=32, nthreads=1):
+    """Timing sample: azimuth planes [ia0, ia1) of one scale -> ((nx, ny, ia1-ia0) complex, seconds spent in
+    the forward stage that a full job pays once per grid)."""
+    rt, ct, cr, pre = _rt(prec)
+    g = np.asfortranarray(grid, dtype=rt)
+    nx, ny = g.shape
+    out = np.empty((nx, ny, ia1 - ia0), ct, order="F")
+    tf = C.c_double(0.0)
+    getattr(lib(), pre + "wlet_planes")(_p(g), C.c_int(nx), C.c_int(ny), cr(dx), cr(dy), cr(kscale), cr(k0), C.c_int(ia0),
+                                        C.c_int(ia1), _p(out), C.c_int(nthreads), C.byref(tf))
+    return out, tf.value
+
+
 def _cube(w, ct):
     w = np.asfortranarray(w, dtype=ct)
     assert w.ndim == 4 and w.shape[2] == NA

@@ -16,6 +16,7 @@
  *   ora_flex_* the flexural model of src/flex/flex.f90 (float64 like the source)
  */
 #include <math.h>
+#include <omp.h>
 #include <stdlib.h>
 #include <string.h>
 

@@ -265,6 +265,41 @@ void FN(wlet_transform)(const REAL *grid, int nx, int ny, REAL dx, REAL dy, cons
     free(ky);
 }
 
+/* A bounded SAMPLE of wlet_transform for timing the CPU path on grids where one full scale takes minutes
+ * (bench.py --impl reference at 4096^2): the azimuth planes [ia0, ia1) of ONE scale, same arithmetic per plane
+ * as above; wt is (nx, ny, ia1-ia0).  *t_forward receives the seconds spent in mirror + demean + forward fourn
+ * (cpwt.f90:94-122), which the full job pays once per grid rather than once per sample. */
+void FN(wlet_planes)(const REAL *grid, int nx, int ny, REAL dx, REAL dy, REAL kscale, REAL k0, int ia0, int ia1,
+                     REAL *wt, int nthreads, double *t_forward)
+{
+    const REAL pi = (REAL)3.141592653589793;
+    int nnx = FN(npow2)(2 * nx), nny = FN(npow2)(2 * ny);
+    size_t P = (size_t)nnx * nny;
+    REAL *ft = (REAL *)malloc(2 * P * sizeof(REAL));
+    REAL *kx = (REAL *)malloc(nnx * sizeof(REAL));
+    REAL *ky = (REAL *)malloc(nny * sizeof(REAL));
+    double t0 = omp_get_wtime();
+    FN(prepare_spectrum)(grid, nx, ny, dx, dy, nnx, nny, ft, kx, ky);
+    if (t_forward) *t_forward = omp_get_wtime() - t0;
+    REAL da = (REAL)2. * XSQRT((REAL)-2. * XLOG((REAL)0.75)) / k0; /* cpwt.f90:131 */
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        REAL *daughter = (REAL *)malloc(2 * P * sizeof(REAL));
+#pragma omp for schedule(dynamic)
+        for (int ia = ia0; ia < ia1; ia++) {
+            REAL kk = kscale * (REAL)1.e3;
+            REAL scales = k0 / kk;
+            REAL angle = (REAL)ia * da - pi / (REAL)2.e0;
+            FN(one_plane)(ft, kx, ky, nx, ny, nnx, nny, k0, scales, angle, daughter, wt + 2 * (size_t)nx * ny * (size_t)(ia - ia0));
+        }
+        free(daughter);
+    }
+    free(ft);
+    free(kx);
+    free(ky);
+}
+
 /* cpwt_sub.f90:107-160 -- running-prefix jackknife of a real (nx,ny,na,ns)
  * array over the azimuth axis. */
 void FN(jackknife_1d_sgram)(const REAL *ss, int nx, int ny, int na, int ns, REAL *ess)

@@ -48,6 +48,11 @@ _SIGS = {
     "pfx_last_error": ([], C.c_char_p),
     "pfx_device_count": ([C.POINTER(_i)], _i),
     "pfx_npow2": ([_i], _i),
+    "pfx_fp64_peak": ([_i, C.POINTER(_d)], _i),
+    "pfx_dev_alloc": ([_i, C.c_size_t, C.POINTER(_vp)], _i),
+    "pfx_dev_free": ([_i, _vp], _i),
+    "pfx_dev_h2d": ([_i, _vp, _vp, C.c_size_t], _i),
+    "pfx_dev_d2h": ([_i, _vp, _vp, C.c_size_t], _i),
     "pfx_plan_create": ([C.POINTER(_vp), _i, _i, _d, _d, _vp, _i, _d, _i, _i], _i),
     "pfx_plan_destroy": ([_vp], _i),
     "pfx_plan_set_stream": ([_vp, _vp], _i),
@@ -113,12 +118,53 @@ def device_count():
     return n.value
 
 
+def fp64_peak(device=None):
+    """Measured FP64 peak (TFLOP/s) of a device: independent DFMA chains, all SMs full."""
+    t = C.c_double()
+    check(lib.pfx_fp64_peak(default_device() if device is None else int(device), C.byref(t)))
+    return t.value
+
+
 def default_device():
     """CUDA ordinal used by the host-pointer API: PLATEFLEX_B200_DEVICE, else LOCAL_RANK, else 0."""
     for var in ("PLATEFLEX_B200_DEVICE", "LOCAL_RANK"):
         if os.environ.get(var, "") != "":
             return int(os.environ[var])
     return 0
+
+
+class DeviceBuffer:
+    """A block of device memory owned by the library (pfx_dev_alloc): lets the Python layer keep
+    intermediate maps on the GPU between calls without depending on a tensor package."""
+
+    def __init__(self, nbytes, device=None):
+        self.device = default_device() if device is None else int(device)
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib.pfx_dev_alloc(self.device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, arr, device=None):
+        buf = cls(arr.nbytes, device)
+        buf.upload(arr)
+        return buf
+
+    def upload(self, arr):
+        assert arr.nbytes <= self.nbytes and (arr.flags.c_contiguous or arr.flags.f_contiguous)
+        check(lib.pfx_dev_h2d(self.device, C.c_void_p(self.ptr), ptr(arr), arr.nbytes))
+
+    def download(self, out, offset=0):
+        assert offset + out.nbytes <= self.nbytes and (out.flags.c_contiguous or out.flags.f_contiguous)
+        check(lib.pfx_dev_d2h(self.device, ptr(out), C.c_void_p(self.ptr + offset), out.nbytes))
+        return out
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib.pfx_dev_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    __del__ = close
 
 
 class Plan:

@@ -15,8 +15,6 @@ Out of scope here (presentation / Bayesian path): the plot_* methods and
 ``inverse='bayes'``; they raise NotImplementedError with a pointer to the
 reference package.
 """
-import sys
-
 import numpy as np
 
 from . import estimate
@@ -190,6 +188,41 @@ class ZcGrid(Grid):
             self.data *= 1.e3
 
 
+def _lazy_map(index, name):
+    """One of the four admittance / coherence maps of a Project as the reference's plain attribute
+    (classes.py:968-971): reading it before ``wlet_admit_coh`` raises AttributeError -- the reference's own
+    probing idiom is ``try: self.wl_admit ... except AttributeError`` (classes.py:1001-1008) -- and the first
+    read after it copies the map from the GPU, where ``estimate_grid`` uses it in place.  Assigning a numpy
+    array replaces the map; the device copy is then dropped and the host arrays are used."""
+    key = "_host_" + name
+
+    def fget(self):
+        h = self.__dict__.get(key)
+        if h is None:
+            d = self.__dict__.get("_dmaps")
+            if d is None:
+                raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
+            h = self.__dict__[key] = d.to_host(index)
+        return h
+
+    def fset(self, value):
+        d = self.__dict__.get("_dmaps")
+        if d is not None:  # keep what the device holds reachable, then let go of it
+            for i, n in enumerate(d.NAMES):
+                if n != name and self.__dict__.get("_host_" + n) is None:
+                    self.__dict__["_host_" + n] = d.to_host(i)
+            d.close()
+            self.__dict__["_dmaps"] = None
+        self.__dict__[key] = value
+
+    def fdel(self):
+        if self.__dict__.get(key) is None and self.__dict__.get("_dmaps") is None:
+            raise AttributeError(name)
+        self.__dict__[key] = None
+
+    return property(fget, fset, fdel)
+
+
 class Project(object):
     """Container of Grid objects (classes.py:635-1332): ``init`` validates, ``wlet_admit_coh``
     computes wavelet admittance / coherence with jackknife errors, ``estimate_cell`` /
@@ -197,6 +230,11 @@ class Project(object):
     after the calls, k, ns, nx, ny, dx, dy, water_depth, rhoc, zc, wl_admit, ewl_admit, wl_coh,
     ewl_coh, mean_Te_grid, std_Te_grid, mean_F_grid, std_F_grid, chi2_grid[, mean_a_grid,
     std_a_grid], new_mask_grid, plus ``status_grid`` (per-cell fit status, new)."""
+
+    wl_admit = _lazy_map(0, "wl_admit")
+    ewl_admit = _lazy_map(1, "ewl_admit")
+    wl_coh = _lazy_map(2, "wl_coh")
+    ewl_coh = _lazy_map(3, "ewl_coh")
 
     def __init__(self, grids=None):
         self.inverse = 'L2'
@@ -289,12 +327,20 @@ class Project(object):
         topo, grav = self._topo_grav()
         have = [hasattr(g, 'wl_trans') for g in (topo, grav)]
         if not any(have):
-            res = fused.wlet_admit_coh(topo.data, grav.data, self.dx, self.dy, self.k)
-        else:
-            for g, h in zip((topo, grav), have):
-                if not h:
-                    g.wlet_transform()
-            res = cpwt.wlet_admit_coh(topo.wl_trans, grav.wl_trans)
+            # maps stay on the GPU; the four attributes are filled from there when first read
+            old = self.__dict__.get("_dmaps")
+            if old is not None:
+                old.close()
+            self.__dict__["_dmaps"] = None
+            dmaps = fused.wlet_admit_coh_device(topo.data, grav.data, self.dx, self.dy, self.k)
+            for n in dmaps.NAMES:
+                self.__dict__["_host_" + n] = None
+            self.__dict__["_dmaps"] = dmaps
+            return
+        for g, h in zip((topo, grav), have):
+            if not h:
+                g.wlet_transform()
+        res = cpwt.wlet_admit_coh(topo.wl_trans, grav.wl_trans)
         self.wl_admit, self.ewl_admit, self.wl_coh, self.ewl_coh = res
         return
 
@@ -309,10 +355,14 @@ class Project(object):
         if not self.initialized:
             raise (Exception('Project not initialized. Aborting'))
         self._check_estimate_args(alph, atype)
-        adm = self.wl_admit[cell[0], cell[1], :]
-        eadm = self.ewl_admit[cell[0], cell[1], :]
-        coh = self.wl_coh[cell[0], cell[1], :]
-        ecoh = self.ewl_coh[cell[0], cell[1], :]
+        dmaps = self.__dict__.get("_dmaps")
+        if dmaps is not None and all(self.__dict__.get("_host_" + n) is None for n in dmaps.NAMES):
+            adm, eadm, coh, ecoh = dmaps.cell(cell[0], cell[1])  # one cell from the GPU, the maps stay there
+        else:
+            adm = self.wl_admit[cell[0], cell[1], :]
+            eadm = self.ewl_admit[cell[0], cell[1], :]
+            coh = self.wl_coh[cell[0], cell[1], :]
+            ecoh = self.ewl_coh[cell[0], cell[1], :]
         # per-cell model parameters go through the module globals, classes.py:1087-1091
         cf_f.wd = self.water_depth[cell[0], cell[1]]
         if self.rhoc is not None:
@@ -344,9 +394,14 @@ class Project(object):
         if parallel:
             raise (Exception('Parallel implementation does not work - ' + 'check again later'))
 
-        res = estimate.L2_estimate_grid(self.k, self.wl_admit, self.ewl_admit, self.wl_coh, self.ewl_coh,
-                                        self.water_depth, rhoc=self.rhoc, zc=self.zc, mask=self.mask, nn=nn,
-                                        alph=alph, atype=atype)
+        dmaps = self.__dict__.get("_dmaps")
+        if dmaps is not None:  # the maps of wlet_admit_coh are still on the GPU: fit them there
+            res = estimate.L2_estimate_grid_device(self.k, dmaps, self.water_depth, rhoc=self.rhoc, zc=self.zc,
+                                                   mask=self.mask, nn=nn, alph=alph, atype=atype)
+        else:
+            res = estimate.L2_estimate_grid(self.k, self.wl_admit, self.ewl_admit, self.wl_coh, self.ewl_coh,
+                                            self.water_depth, rhoc=self.rhoc, zc=self.zc, mask=self.mask, nn=nn,
+                                            alph=alph, atype=atype)
         if self.mask is not None:
             # classes.py:1185-1187,1229: decimated copy of the mask over the visited cells
             new_mask_grid = np.zeros((int(self.nx / nn), int(self.ny / nn)), dtype=bool)
@@ -462,19 +517,3 @@ def _lam2k(nx, ny, dx, dy, p=0.85):
         dk = half_width / s
     lam = np.array(lam)
     return len(lam), np.array(2. * np.pi / lam)
-
-
-def _progressbar(it, prefix="", size=60, file=sys.stdout):
-    """classes.py:1831-1844 (kept for callers that import it)."""
-    count = len(it)
-
-    def show(j):
-        x = int(size * j / count)
-        file.write("%s[%s%s] %i/%i\r" % (prefix, "#" * x, "." * (size - x), j, count))
-        file.flush()
-    show(0)
-    for i, item in enumerate(it):
-        yield item
-        show(i + 1)
-    file.write("\n")
-    file.flush()

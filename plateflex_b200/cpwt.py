@@ -176,4 +176,64 @@ class _Fused:
         return tuple(outs)
 
 
+    def wlet_admit_coh_device(self, topo, grav, dx, dy, kf):
+        """Same transform, results left on the GPU: returns a DeviceMaps holding wl_admit, ewl_admit, wl_coh,
+        ewl_coh as (nx, ny, ns) float64 device arrays (x fastest).  Project.wlet_admit_coh uses it so that
+        Project.estimate_grid can fit the maps where they are; a map crosses to the host only when read."""
+        g1, g2 = _grid(topo, "topo"), _grid(grav, "grav")
+        if g1.shape != g2.shape:
+            raise ValueError("grids must have the same shape")
+        kf = np.ascontiguousarray(kf, dtype=np.float64).ravel()
+        nx, ny = g1.shape
+        plan = _lib.get_plan(nx, ny, dx, dy, kf, conf_cpwt.k0)
+        maps = DeviceMaps(nx, ny, len(kf), plan.device)
+        d_in = [_lib.DeviceBuffer.from_host(g, plan.device) for g in (g1, g2)]
+        try:
+            _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, C.c_void_p(d_in[0].ptr), C.c_void_p(d_in[1].ptr), 0,
+                                                       len(kf), *[C.c_void_p(p) for p in maps.ptrs()]))
+            maps.synchronize()
+        finally:
+            for b in d_in:
+                b.close()
+        return maps
+
+
+class DeviceMaps:
+    """Four (nx, ny, ns) float64 maps resident on one GPU, in the order wl_admit, ewl_admit, wl_coh, ewl_coh."""
+
+    NAMES = ("wl_admit", "ewl_admit", "wl_coh", "ewl_coh")
+
+    def __init__(self, nx, ny, ns, device):
+        self.nx, self.ny, self.ns, self.device = int(nx), int(ny), int(ns), int(device)
+        self.map_bytes = self.nx * self.ny * self.ns * 8
+        self.buf = _lib.DeviceBuffer(4 * self.map_bytes, device)
+        self.out_dtype = _OUT_DTYPE  # the output dtype in force when the maps were computed (set_output_dtype)
+
+    def ptrs(self):
+        return [self.buf.ptr + i * self.map_bytes for i in range(4)]
+
+    def synchronize(self):
+        # a zero-byte-free way to wait for the plan's (legacy default) stream: a tiny synchronous copy
+        probe = np.empty(1)
+        self.buf.download(probe)
+
+    def to_host(self, index):
+        out = np.empty((self.nx, self.ny, self.ns), dtype=np.float64, order="F")
+        self.buf.download(out, index * self.map_bytes)
+        return out.astype(np.float32) if self.out_dtype == np.float32 else out
+
+    def cell(self, i, j):
+        """The ns values of every map at grid cell (i, j): four length-ns vectors, without moving the maps."""
+        i, j = int(i) % self.nx, int(j) % self.ny
+        out = np.empty((4, self.ns))
+        one = np.empty(1)
+        for m in range(4):
+            for s in range(self.ns):
+                out[m, s] = self.buf.download(one, m * self.map_bytes + ((s * self.ny + j) * self.nx + i) * 8)[0]
+        return out.astype(np.float32).astype(np.float64) if self.out_dtype == np.float32 else out
+
+    def close(self):
+        self.buf.close()
+
+
 fused = _Fused()

@@ -41,6 +41,26 @@ struct DeviceGuard {
 
 using namespace pfx;
 
+namespace {
+// independent FMA chains: every thread keeps 8 accumulators busy, 32 fused multiply-adds per loop trip
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double x, double y)
+{
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = (double)(threadIdx.x + j) * 1e-3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = fma(a[j], x, y);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += a[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
 int pfx_plan::alloc(void **p, size_t bytes)
 {
     *p = nullptr;
@@ -127,6 +147,80 @@ int pfx_npow2(int n)
     do n2 *= 2;
     while (n2 < n);
     return n2;
+}
+
+int pfx_fp64_peak(int device, double *tflops)
+{
+    PFX_ARG(tflops, "tflops is null");
+    DeviceGuard guard(device);
+    PFX_ARG(guard.ok, "device ordinal out of range");
+    int nsm = 0;
+    PFX_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = nsm * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    PFX_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {  // first trip warms up; best of the rest
+        cudaEventRecord(e0, 0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) {
+        set_error("fp64 peak kernel failed: %s", cudaGetErrorString(e));
+        return PFX_ERR_CUDA;
+    }
+    *tflops = 2.0 * 32.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return PFX_OK;
+}
+
+int pfx_dev_alloc(int device, size_t bytes, void **dev_ptr)
+{
+    PFX_ARG(dev_ptr, "dev_ptr is null");
+    *dev_ptr = nullptr;
+    DeviceGuard guard(device);
+    PFX_ARG(guard.ok, "device ordinal out of range");
+    cudaError_t e = cudaMalloc(dev_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PFX_ERR_OOM : PFX_ERR_CUDA;
+    }
+    return PFX_OK;
+}
+
+int pfx_dev_free(int device, void *dev_ptr)
+{
+    DeviceGuard guard(device);
+    if (dev_ptr) PFX_CUDA(cudaFree(dev_ptr));
+    return PFX_OK;
+}
+
+int pfx_dev_h2d(int device, void *dst_dev, const void *src_host, size_t bytes)
+{
+    PFX_ARG(dst_dev && src_host, "null pointer");
+    DeviceGuard guard(device);
+    PFX_CHECK(staged_h2d(dst_dev, src_host, bytes, 0));
+    PFX_CUDA(cudaStreamSynchronize(0));
+    return PFX_OK;
+}
+
+int pfx_dev_d2h(int device, void *dst_host, const void *src_dev, size_t bytes)
+{
+    PFX_ARG(dst_host && src_dev, "null pointer");
+    DeviceGuard guard(device);
+    PFX_CHECK(staged_d2h(dst_host, src_dev, bytes, 0));  // synchronous
+    return PFX_OK;
 }
 
 int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, const double *k_rad_m, int ns, double k0,

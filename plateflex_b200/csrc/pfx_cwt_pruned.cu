@@ -29,6 +29,7 @@
 #include "pfx_plan.hpp"
 #include "pfx_pruned.hpp"
 #include "pfx_pruned_v2.cuh"
+#include "pfx_pruned_v3.cuh"
 
 namespace pfx {
 
@@ -159,6 +160,9 @@ struct PrunedState {
     int ctas_per_transform = 128;
     // second-generation kernels (pfx_pruned_v2.cuh), chosen per scale and axis: variant < 0 = first generation
     std::vector<int> v2x, v2y, v2x_ctas, v2y_ctas;
+    // third-generation pass 2 (pfx_pruned_v3.cuh): line buffers in the ring (0 = not used for this scale)
+    std::vector<int> v3x_nbuf, v3x_ctas, v3y_nbuf, v3y_ctas;
+    int v3_occ = 3;  // CTAs per SM the v3 kernels are compiled for (PLATEFLEX_B200_V3_OCC = 2 | 3)
     int nsm = 148;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
     std::vector<std::pair<void *, size_t>> owned;
@@ -210,6 +214,22 @@ int plan_init_pruned(pfx_plan *pl)
     st->v2y.assign(ns, -1);
     st->v2x_ctas.assign(ns, 0);
     st->v2y_ctas.assign(ns, 0);
+    st->v3x_nbuf.assign(ns, 0);
+    st->v3x_ctas.assign(ns, 0);
+    st->v3y_nbuf.assign(ns, 0);
+    st->v3y_ctas.assign(ns, 0);
+    // PLATEFLEX_B200_V3 = "on" | "1" | "2" (ring depth): third-generation pass kernels with bulk-copy staged support
+    // samples.  Opt-in: they need the intermediate transposed, and the scattered stores that costs pass 1 outweigh
+    // what pass 2 gains on B200 (measured, profiles/README.md), so the second generation stays the default.
+    const char *v3_env = getenv("PLATEFLEX_B200_V3");
+    const bool v3_on = v3_env && (!strcmp(v3_env, "on") || v3_env[0] == '1' || v3_env[0] == '2');
+    const int v3_depth = (v3_env && (v3_env[0] == '1' || v3_env[0] == '2')) ? v3_env[0] - '0' : 0;
+    const char *v3p1_env = getenv("PLATEFLEX_B200_V3_P1");  // "off": second-generation pass 1
+    const bool v3p1_on = v3_on && !(v3p1_env && !strcmp(v3p1_env, "off"));
+    {
+        const char *o = getenv("PLATEFLEX_B200_V3_OCC");
+        if (o && (o[0] == '2' || o[0] == '3')) st->v3_occ = o[0] - '0';
+    }
     PFX_CUDA(cudaDeviceGetAttribute(&st->nsm, cudaDevAttrMultiProcessorCount, pl->device));
     // PLATEFLEX_B200_V2 = "off" | "<lines per CTA 1|2>,<prefetch 0|1>"  (default "1,0")
     bool v2_on = true;
@@ -222,7 +242,7 @@ int plan_init_pruned(pfx_plan *pl)
             v2_pre = (e[2] == '1') ? 1 : 0;
         }
     }
-    size_t tabu_n = 0, tabv_n = 0, twa_n = 0, twb_n = 0, kamax_all = 0;
+    size_t tabu_n = 0, tabv_n = 0, twa_n = 0, twb_n = 0, t_elems = 0;
     std::vector<int> h_lo((size_t)ns * 4 * PFX_NA);
     for (int is = 0; is < ns; is++) {
         ScaleDesc &sd = st->sd[is];
@@ -272,7 +292,10 @@ int plan_init_pruned(pfx_plan *pl)
         tabv_n += (size_t)PFX_NA * sd.ay.L;
         twa_n += (size_t)PFX_NA * NX;
         twb_n += (size_t)PFX_NA * NY;
-        kamax_all = std::max(kamax_all, (size_t)sd.kamax);
+        // v3 pass 2 (same conditions as v2, single line per CTA): T is stored transposed, one line of LP slots per row
+        if (v3_on && st->v2x[is] >= 0) st->v3x_nbuf[is] = 1;  // ring depth settled below (occupancy)
+        if (v3p1_on && st->v2y[is] >= 0) st->v3y_nbuf[is] = 1;
+        t_elems = std::max(t_elems, st->v3x_nbuf[is] ? (size_t)ny * v3_line_slots(sd.ax.logL) : (size_t)sd.kamax * ny);
         if (st->v2y[is] < 0) st->smem1 = std::max(st->smem1, prn_smem_bytes(sd.ay, 1));
         if (st->v2x[is] < 0) st->smem2 = std::max(st->smem2, prn_smem_bytes(sd.ax, st->cpc));
     }
@@ -287,7 +310,7 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CHECK(dalloc((void **)&st->tabv, tabv_n * sizeof(double)));
     PFX_CHECK(dalloc((void **)&st->twa, twa_n * sizeof(double2)));
     PFX_CHECK(dalloc((void **)&st->twb, twb_n * sizeof(double2)));
-    PFX_CHECK(dalloc((void **)&st->T, 2 * PFX_NA * kamax_all * ny * sizeof(double2)));
+    PFX_CHECK(dalloc((void **)&st->T, 2 * PFX_NA * t_elems * sizeof(double2)));
     for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Wbuf[b], 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
     st->W = st->Wbuf[0];
     PFX_CHECK(dalloc((void **)&st->zc, (size_t)nx * ny * sizeof(double2)));
@@ -357,13 +380,46 @@ int plan_init_pruned(pfx_plan *pl)
     for (int is = 0; is < ns; is++) {
         const ScaleDesc &sd = st->sd[is];
         int res = 0;
-        if (st->v2y[is] >= 0) {
+        if (st->v3y_nbuf[is]) {
+            const int multi = (st->v2y[is] >> 5) & 1, half = 2 * ny == NY;
+            int nbuf = v3_depth ? v3_depth : 2;
+            PFX_CHECK(v3_configure_p1(sd.ay.logL, multi, half, st->v3_occ, nbuf, &res));
+            if (!v3_depth && res < st->v3_occ) {
+                int res1 = 0;
+                PFX_CHECK(v3_configure_p1(sd.ay.logL, multi, half, st->v3_occ, 1, &res1));
+                if (res1 > res) {
+                    nbuf = 1;
+                    res = res1;
+                } else {
+                    PFX_CHECK(v3_configure_p1(sd.ay.logL, multi, half, st->v3_occ, 2, &res));
+                }
+            }
+            st->v3y_nbuf[is] = nbuf;
+            st->v3y_ctas[is] = std::max(res, 1) * st->nsm;
+        } else if (st->v2y[is] >= 0) {
             PFX_CHECK(v2_configure_p1(sd.ay.logL, st->v2y[is], &res));
             st->v2y_ctas[is] = std::max(res, 1) * st->nsm;
         } else {
             PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
         }
-        if (st->v2x[is] >= 0) {
+        if (st->v3x_nbuf[is]) {
+            // two line buffers when three CTAs per SM still fit, else one (refilled behind the first stage)
+            const int multi = (st->v2x[is] >> 5) & 1, half = 2 * nx == NX;
+            int nbuf = v3_depth ? v3_depth : 2;
+            PFX_CHECK(v3_configure_p2(sd.ax.logL, multi, half, st->v3_occ, nbuf, &res));
+            if (!v3_depth && res < st->v3_occ) {
+                int res1 = 0;
+                PFX_CHECK(v3_configure_p2(sd.ax.logL, multi, half, st->v3_occ, 1, &res1));
+                if (res1 > res) {
+                    nbuf = 1;
+                    res = res1;
+                } else {
+                    PFX_CHECK(v3_configure_p2(sd.ax.logL, multi, half, st->v3_occ, 2, &res));
+                }
+            }
+            st->v3x_nbuf[is] = nbuf;
+            st->v3x_ctas[is] = std::max(res, 1) * st->nsm;
+        } else if (st->v2x[is] >= 0) {
             PFX_CHECK(v2_configure_p2(sd.ax.logL, st->v2x[is], &res));
             st->v2x_ctas[is] = std::max(res, 1) * st->nsm;
         } else {
@@ -430,6 +486,11 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     a.rooty = st->rooty;
     a.T = st->T;
     a.W = st->W;
+    if (st->v3x_nbuf[is]) {
+        a.t_tr = 1;
+        a.t_lp = v3_line_slots(a.sd.ax.logL);
+        a.t_pad = v3_pad(a.sd.ax.logL);
+    }
     const ScaleDesc &sd = a.sd;
     const size_t sm1 = prn_smem_bytes(sd.ay, 1), sm2 = prn_smem_bytes(sd.ax, st->cpc);
     const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
@@ -439,7 +500,14 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     const char *ctas_env = getenv("PLATEFLEX_B200_CTAS");
     {
         ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
-        if (st->v2y[is] >= 0) {
+        if (st->v3y_nbuf[is]) {
+            const int multi = (st->v2y[is] >> 5) & 1;
+            v3::V3Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1), st->v3y_nbuf[is]};
+            // a few waves: the number of columns differs between azimuths
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v3y_ctas[is] / ntr);
+            PFX_CHECK(v3_launch_p1(va, sd.ay.logL, multi, 2 * pl->ny == pl->NY, st->v3_occ, dim3(std::min(sd.kamax, ctas), ntr),
+                                   pl->stream));
+        } else if (st->v2y[is] >= 0) {
             v2::V2Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
             const int cpc = st->v2y[is] & 15, groups = (sd.kamax + cpc - 1) / cpc;
             // a few waves: the number of columns differs between azimuths
@@ -451,7 +519,13 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     }
     {
         ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
-        if (st->v2x[is] >= 0) {
+        if (st->v3x_nbuf[is]) {
+            const int multi = (st->v2x[is] >> 5) & 1;
+            v3::V3Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1), st->v3x_nbuf[is]};
+            // every transform has the same number of rows: one wave of persistent CTAs
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v3x_ctas[is] / ntr);
+            PFX_CHECK(v3_launch_p2(va, sd.ax.logL, multi, 2 * pl->nx == pl->NX, st->v3_occ, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+        } else if (st->v2x[is] >= 0) {
             v2::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
             const int cpc = st->v2x[is] & 15, groups = (pl->ny + cpc - 1) / cpc;
             // every transform has the same number of rows: one wave of persistent CTAs when a line is a single

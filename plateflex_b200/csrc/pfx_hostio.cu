@@ -7,6 +7,8 @@
 // memory takes the plain cudaMemcpyAsync path.
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -39,7 +41,21 @@ struct Staging {
         return ok = true;
     }
 };
-Staging g_stage;
+// One Staging per device ordinal: its events belong to the device that is current when they are created, and
+// a copy may only record them on streams of that device.  Copies to different devices do not serialise on
+// each other; the state lives until the process exits (pinned memory is freed with the context).
+std::mutex g_stage_mu;
+std::map<int, std::unique_ptr<Staging>> g_stages;
+
+Staging &stage_of_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError();
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    std::unique_ptr<Staging> &p = g_stages[dev];
+    if (!p) p.reset(new Staging());
+    return *p;
+}
 
 int team_size()
 {
@@ -87,6 +103,7 @@ int staged_d2h(void *dst, const void *src_dev, size_t bytes, cudaStream_t st)
         PFX_CUDA(cudaStreamSynchronize(st));
         return PFX_OK;
     }
+    Staging &g_stage = stage_of_current_device();  // the caller holds a DeviceGuard of the stream's device
     std::lock_guard<std::mutex> lock(g_stage.mu);
     if (!g_stage.init()) {
         PFX_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st));
@@ -118,6 +135,7 @@ int staged_h2d(void *dst_dev, const void *src, size_t bytes, cudaStream_t st)
         PFX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));
         return PFX_OK;
     }
+    Staging &g_stage = stage_of_current_device();
     std::lock_guard<std::mutex> lock(g_stage.mu);
     if (!g_stage.init()) {
         PFX_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, st));

@@ -65,7 +65,11 @@ struct PrunedArgs {
     const double *tabu, *tabv;     // weight tables (all scales)
     const double2 *twa, *twb;      // stage-1 twiddle tables (all scales)
     const double2 *rootx, *rooty;  // exp(2 pi i m / N)
-    double2 *T;                    // [t][ka row][j]  intermediate, t = ia + 11*g
+    double2 *T;                    // intermediate, t = ia + 11*g: [t][ka row][j], or with t_tr [t][j][slot]
+    // t_tr: pass 1 writes T transposed, one contiguous line of t_lp slots per output row j, the sample of
+    // wavenumber index a at slot n + (t_pad ? n >> 3 : 0), n = a mod Lx -- the order in which the first stage
+    // of the third-generation pass 2 (pfx_pruned_v3.cuh) reads it after one bulk copy of the line
+    int t_tr = 0, t_lp = 0, t_pad = 0;
     double2 *W;                    // [t][j][i] output planes (main Gaussian term only)
 };
 
@@ -74,6 +78,19 @@ inline size_t prn_smem_bytes(const AxisDesc &A, int cpc)
 {
     return (prn_plane_elems(A) * cpc + (A.r > 1 ? (size_t)A.L * cpc : 0) + prn_stw_total(A.logL) + 2 * (size_t)A.rc) *
            sizeof(double2);
+}
+
+// element offset in T of output j of support column m (wavenumber index alo + m) of transform t, split into
+// the part that is fixed for a column and the stride between consecutive j
+__host__ __device__ inline size_t prn_t_column(const PrunedArgs &a, int t, int m, int alo, size_t &jstride)
+{
+    if (a.t_tr) {
+        const int n = (alo + m) & (a.sd.ax.L - 1);
+        jstride = (size_t)a.t_lp;
+        return (size_t)t * a.ny * a.t_lp + (size_t)(n + (a.t_pad ? (n >> 3) : 0));
+    }
+    jstride = 1;
+    return ((size_t)t * a.sd.kamax + m) * a.ny;
 }
 
 // launchers, one translation unit each (pfx_pruned_p1.cu, pfx_pruned_p2.cu)

@@ -272,14 +272,15 @@ __global__ void __launch_bounds__(NT, 3) pass1_kernel(PrunedArgs a)
             for (int mb = threadIdx.x; mb < K; mb += NT) y[mb] = from_global(0, mb);
         __syncthreads();
         const double wu = a.tabu[sd.tabu + (size_t)ia * sd.ax.L + m];
-        double2 *Trow = a.T + ((size_t)t * sd.kamax + m) * a.ny;
+        size_t tjs;
+        double2 *Trow = a.T + prn_t_column(a, t, m, sd.alo[ia], tjs);
         for (int part = 0; part < nsplit; part++) {
             const int rho0 = part << A.logrc;
             if (nsplit > 1) {
                 load_residue_factors<LOGL>(gt, ht, A, rho0, a.rooty);
                 __syncthreads();
             }
-            auto store = [&](int, int j, double2 v) { Trow[j] = make_double2(v.x * wu, v.y * wu); };
+            auto store = [&](int, int j, double2 v) { Trow[(size_t)j * tjs] = make_double2(v.x * wu, v.y * wu); };
             if (staged)
                 fft_lines<LOGL, 1, PAD>(sm, from_smem, store, A, plane, lo, K, rho0, tw, tb);
             else

@@ -330,7 +330,9 @@ struct Pass1Group {
     const double2 *spec;  // padded spectrum [a][b] (y-wavenumber fastest)
     const double *tv;     // v1 weights of this azimuth [L]
     const double *tu;     // (c/P) u1 weights of this azimuth [Lx]
-    double2 *Tt;          // T[t][m][j]
+    double2 *T;           // intermediate (layout: prn_t_column)
+    const PrunedArgs *pa;
+    int t;
     int NX, NYm, ny, alo, ka, blo, ngroups, logr;
     __device__ __forceinline__ int first() const { return blockIdx.x; }
     __device__ __forceinline__ bool valid(int g) const { return g < ngroups; }
@@ -348,7 +350,9 @@ struct Pass1Group {
         const int j = (q << logr) + rho, m = g * CPC + c;
         if (j < ny && (CPC == 1 || m < ka)) {
             const double wu = tu[m];
-            Tt[(size_t)m * ny + j] = make_double2(v.x * wu, v.y * wu);
+            size_t js;
+            const size_t o = prn_t_column(*pa, t, m, alo, js);
+            T[o + (size_t)j * js] = make_double2(v.x * wu, v.y * wu);
         }
     }
 };
@@ -369,7 +373,9 @@ __global__ void __launch_bounds__(NT, (CPC == 1 && !PREFETCH && !MULTI) ? 3 : 2)
     grp.spec = g ? a.p.spec1 : a.p.spec0;
     grp.tv = a.p.tabv + sd.tabv + ((size_t)ia << LOGL);
     grp.tu = a.p.tabu + sd.tabu + (size_t)ia * sd.ax.L;
-    grp.Tt = a.p.T + (size_t)t * sd.kamax * a.p.ny;
+    grp.T = a.p.T;
+    grp.pa = &a.p;
+    grp.t = t;
     grp.NX = a.p.NX;
     grp.NYm = a.p.NY - 1;
     grp.ny = a.p.ny;

@@ -8,6 +8,8 @@
 // HBM traffic per cell and scale: 11 (or 22) coalesced 16-byte loads and 2-4
 // 8-byte stores; consecutive threads own consecutive x so every warp reads and
 // writes whole 128-byte lines.
+#include <cstdlib>
+
 #include "pfx_common.cuh"
 
 namespace pfx {
@@ -68,6 +70,18 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
     return jk_spread(v2);
 }
 
+// The same two quotients added straight into the running sums of the walk (sa += ad, sc += co) with one fused
+// multiply-add each: when a sum is 0 the common factor is replaced by 0, so both sums stay as they are.
+__device__ __forceinline__ void ratio_acc(double q1, double q2, double qx, double &sa, double &sc)
+{
+    const double prod = q1 * q2;
+    const double xr = qx * fast_rcp(prod);
+    const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
+    const double f = ok ? xr : 0.0;
+    sc = fma(qx, f, sc);
+    sa = fma(q2, f, sa);
+}
+
 __device__ __forceinline__ void ratio(double q1, double q2, double qx, double &ad, double &co)
 {
     // cpwt_sub.f90:329-335: co = Re(xp)^2/(p1*p2), ad = Re(xp)/p1, both 0 when a sum is 0.
@@ -98,10 +112,7 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             q1 += s1[a2];
             q2 += s2[a2];
             qx += xr[a2];
-            double ad, co;
-            ratio(q1, q2, qx, ad, co);
-            sa += ad;
-            sc += co;
+            ratio_acc(q1, q2, qx, sa, sc);
         }
         ad2[a] = sa * (1.0 / (double)(NA - 1));
         co2[a] = sc * (1.0 / (double)(NA - 1));
@@ -109,10 +120,7 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             p1 += s1[a];
             p2 += s2[a];
             px += xr[a];
-            double ad, co;
-            ratio(p1, p2, px, ad, co);
-            cad += ad;
-            cco += co;
+            ratio_acc(p1, p2, px, cad, cco);
         }
     }
     ead = jk_spread(ad2);
@@ -142,8 +150,8 @@ __device__ __forceinline__ void put(double *base, size_t o, double v)
         base[o] = v;
 }
 
-template <int MODE, bool SHARDED, bool F32>
-__global__ void __launch_bounds__(128, 4)
+template <int MODE, bool SHARDED, bool F32, int OCC = 4>
+__global__ void __launch_bounds__(128, OCC)
     reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
                   double *__restrict__ out2, double *__restrict__ out3, ShardOut sh)
 {
@@ -237,10 +245,18 @@ int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *
 {
     dim3 block(128), grid((nx + 127) / 128, ny);
     const ShardOut none;
+    static const int occ = [] {  // CTAs of 128 threads per SM the admittance / coherence epilogue is compiled for
+        const char *e = getenv("PLATEFLEX_B200_REDUCE_OCC");
+        return (e && e[0] == '3') ? 3 : 4;
+    }();
     if (shards && shards->nshards > 0) {
         PFX_ARG(mode == RED_ADMIT_COH && !f32, "row-sharded output exists for the float64 admittance / coherence epilogue only");
-        reduce_kernel<RED_ADMIT_COH, true, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
-                                                                           nullptr, *shards);
+        if (occ == 3)
+            reduce_kernel<RED_ADMIT_COH, true, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
+                                                                                  nullptr, *shards);
+        else
+            reduce_kernel<RED_ADMIT_COH, true, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
+                                                                               nullptr, *shards);
         PFX_CUDA(cudaGetLastError());
         return PFX_OK;
     }
@@ -258,6 +274,8 @@ int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *
         case RED_ADMIT_COH:
             if (f32)
                 reduce_kernel<RED_ADMIT_COH, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            else if (occ == 3)
+                reduce_kernel<RED_ADMIT_COH, false, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             else
                 reduce_kernel<RED_ADMIT_COH, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
             break;

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from .flex import conf_flex, flex
 
-__all__ = ["L2_estimate_cell", "L2_estimate_grid", "get_L2_estimates", "real_xspec_functions"]
+__all__ = ["L2_estimate_cell", "L2_estimate_grid", "L2_estimate_grid_device", "get_L2_estimates", "real_xspec_functions"]
 
 STATUS_TEXT = {0: "not fitted", 1: "converged", 2: "max_nfev reached", 3: "non-finite data or zero sigma"}
 
@@ -67,6 +67,55 @@ def L2_estimate_grid(k, wl_admit, ewl_admit, wl_coh, ewl_coh, wd, rhoc=None, zc=
         *[_lib.ptr(out.get(n)) for n in names], _lib.ptr(status)))
     out["status"] = status & 0xff
     out["nfev"] = status >> 8  # model evaluations per cell (least_squares' nfev)
+    _report(out["status"], strict)
+    return out
+
+
+def L2_estimate_grid_device(k, dmaps, wd, rhoc=None, zc=None, mask=None, nn=1, alph=False, atype="joint",
+                            strict=False):
+    """``L2_estimate_grid`` on maps that are already on the GPU (a cpwt.DeviceMaps, what
+    Project.wlet_admit_coh leaves behind): only wd / rhoc / zc / mask go up and only the
+    (nx//nn, ny//nn) result maps come back."""
+    _check_args(alph, atype)
+    k = np.ascontiguousarray(k, dtype=np.float64).ravel()
+    nx, ny, ns, dev = dmaps.nx, dmaps.ny, dmaps.ns, dmaps.device
+    if ns != len(k):
+        raise ValueError("admittance / coherence maps must all have shape (nx, ny, len(k))")
+
+    def up(a, name, dtype=np.float64):
+        if a is None:
+            return None
+        a = np.asfortranarray(a, dtype=dtype)
+        if a.shape != (nx, ny):
+            raise ValueError(f"{name} must have shape ({nx}, {ny})")
+        return _lib.DeviceBuffer.from_host(a, dev)
+
+    mx, my = nx // nn, ny // nn
+    names = ["mean_Te", "std_Te", "mean_F", "std_F", "mean_a", "std_a", "chi2"]
+    want = [n for n in names if alph or not n.endswith("_a")]
+    bufs = {"k": _lib.DeviceBuffer.from_host(k, dev), "wd": up(wd, "wd"), "rhoc": up(rhoc, "rhoc"), "zc": up(zc, "zc"),
+            "mask": up(mask, "mask", np.uint8) if mask is not None else None,
+            "out": _lib.DeviceBuffer(max(mx * my, 1) * 8 * len(want), dev), "status": _lib.DeviceBuffer(max(mx * my, 1) * 4, dev)}
+    try:
+        p = lambda b: C.c_void_p(b.ptr) if b is not None else None
+        optr = {n: C.c_void_p(bufs["out"].ptr + i * mx * my * 8) for i, n in enumerate(want)}
+        conf = conf_flex.as_struct()
+        _lib.check(_lib.lib.pfx_l2_fit_dev(
+            dev, None, C.byref(conf), p(bufs["k"]), ns, nx, ny, *[C.c_void_p(q) for q in dmaps.ptrs()], p(bufs["wd"]),
+            p(bufs["rhoc"]), p(bufs["zc"]), p(bufs["mask"]), int(nn), int(alph), _lib.ATYPES[atype],
+            *[optr.get(n) for n in names], p(bufs["status"])))
+        out = {}
+        for i, n in enumerate(want):
+            out[n] = bufs["out"].download(np.zeros((mx, my), order="F"), i * mx * my * 8) if mx * my else np.zeros((mx, my), order="F")
+        status = np.zeros((mx, my), dtype=np.int32, order="F")
+        if mx * my:
+            bufs["status"].download(status)
+    finally:
+        for b in bufs.values():
+            if b is not None:
+                b.close()
+    out["status"] = status & 0xff
+    out["nfev"] = status >> 8
     _report(out["status"], strict)
     return out
 

@@ -16,7 +16,8 @@ CPU tensors with the gloo backend (tests/test_sharding.py) and on CUDA tensors w
 import torch
 import torch.distributed as dist
 
-__all__ = ["scale_range", "balanced_cuts", "deal_scales", "row_range", "rows_per_shard", "RowResharder", "PeerShards", "gather_rows"]
+__all__ = ["scale_range", "balanced_cuts", "deal_scales", "row_range", "rows_per_shard", "RowResharder", "PeerShards", "gather_rows",
+           "gather_rows_to_root", "stream_barrier", "TeMapPipeline"]
 
 
 def scale_range(ns, world, rank, cost=None):
@@ -192,7 +193,19 @@ class PeerShards:
         stride = self.ns * self.nrows * self.nx * 8
         return [self.own.value + m * stride for m in range(4)]
 
+    def fence(self):
+        """All ranks: everything enqueued so far has completed everywhere.  Needed (a) after the transforms,
+        before any rank's fit reads its shard (peers store into it), (b) after the fits, before the next
+        transform's remote stores overwrite a shard that is still being read, (c) before ``close`` frees memory
+        other ranks have mapped.  ``stream_barrier`` is the stream-ordered form of (a) / (b) that does not
+        block the host."""
+        import torch
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
     def close(self):
+        if self.world > 1 and dist.is_initialized():
+            self.fence()  # no peer may still be storing into (or have work pending on) a buffer about to go
         for p in self._opened:
             self._lib.lib.pfx_ipc_close(self.device, p)
         self._opened = []
@@ -215,3 +228,166 @@ def gather_rows(local, nx_out, out_rows, group=None):
     for q in range(world):
         pieces[q] = bufs[q][:nx_out * out_rows[q]]
     return torch.cat(pieces)
+
+
+def stream_barrier(flag, group=None):
+    """Stream-ordered barrier: a one-element all-reduce on the current stream.  Work enqueued after it on any
+    rank starts only when every rank's stream has reached it -- without blocking the host, so a pipeline of
+    several steps keeps streaming.  ``flag`` is a one-element tensor on the device (CPU tensors with gloo)."""
+    dist.all_reduce(flag, group=group)
+
+
+def gather_rows_to_root(local, nmaps, mx, out_rows, dst=0, group=None):
+    """Rank ``dst`` receives the concatenation along y of every rank's (nmaps, out_rows[rank], mx) block
+    (flat, x fastest) as one (nmaps, sum(out_rows), mx) tensor; other ranks get None.  One collective for all
+    maps; shards are padded to the tallest one because gather wants equal sizes."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rmax = max(out_rows)
+    mine = out_rows[rank]
+    padded = local.new_zeros((nmaps, rmax, mx))
+    if mine:
+        padded[:, :mine, :].copy_(local[:nmaps * mine * mx].view(nmaps, mine, mx))
+    bufs = [local.new_empty((nmaps, rmax, mx)) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:, :r, :] for b, r in zip(bufs, out_rows)], dim=1).contiguous()
+
+
+class TeMapPipeline:
+    """The whole hot path on ``world`` GPUs of one node: two (nx, ny) grids on rank 0 in, the fitted
+    (Te, std Te, F, std F[, alpha, std alpha], chi2) maps and the per-cell status on rank 0 out
+    (Project.wlet_admit_coh + Project.estimate_grid, classes.py:916-975, 1125-1332).
+
+      1. rank 0 broadcasts topography, gravity and water depth (NCCL);
+      2. every rank transforms the scales dealt to it by cost (pfx_plan_scale_cost, longest first) and the
+         epilogue of each scale stores its output rows straight into the row shard of the GPU that will fit
+         them, over NVLink through CUDA-IPC mappings (PeerShards) -- the exchange is fused with the
+         epilogue, no pack kernel and no collective on the data path;
+      3. a stream-ordered barrier (one-element all-reduce): all shards are complete;
+      4. every rank fits the cells of its rows (pfx_l2_fit_rows_dev);
+      5. the result maps are gathered on rank 0 (one NCCL gather).
+    The broadcast of the next step cannot overtake the gather of this one on rank 0, so no rank starts
+    storing into a shard that is still being fitted.  With world == 1 there is nothing to exchange: the
+    plain single-GPU entry points run (pfx_wlet_admit_coh_dev + pfx_l2_fit_dev).
+    Everything is enqueued on the current CUDA stream of each rank; torch carries buffers and collectives."""
+
+    def __init__(self, nx, ny, dx, dy, k, k0, conf, alph=False, atype="joint", nn=1, local_device=0, engine=None,
+                 group=None, balance="deal", solo=False):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        self._lib, self._C = _lib, C
+        # solo: this process alone, whatever process group exists (independent replicas, reference runs)
+        multi = dist.is_initialized() and not solo
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        self.group, self.local = group, int(local_device)
+        self.nx, self.ny, self.ns, self.nn = int(nx), int(ny), len(k), int(nn)
+        self.alph, self.atype, self.conf = bool(alph), atype, conf
+        self.dev = torch.device("cuda", self.local)
+        self.plan = _lib.Plan(nx, ny, dx, dy, k, k0, engine=_lib.default_engine() if engine is None else engine,
+                              device=self.local)
+        self.d_k = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).to(self.dev)
+        self.cost = self.plan.scale_cost()
+        nxy = self.nx * self.ny
+        self.d_topo = torch.empty(nxy, dtype=torch.float64, device=self.dev)
+        self.d_grav = torch.empty(nxy, dtype=torch.float64, device=self.dev)
+        self.d_wd = torch.empty(nxy, dtype=torch.float64, device=self.dev)  # (nx, ny) x fastest: [j][i]
+        self.nmaps = 7 if self.alph else 5
+        self.mx = self.nx // self.nn
+        if self.world > 1:
+            self.peers = PeerShards(nx, ny, self.ns, self.world, self.rank, self.local, group=group)
+            self.row0, self.nrows = self.peers.row0, self.peers.nrows
+            if balance == "deal":
+                self.scales = deal_scales(self.cost, self.world)[self.rank]
+            else:
+                a, b = scale_range(self.ns, self.world, self.rank, self.cost)
+                self.scales = list(range(a, b))
+            self.map_ptrs = self.peers.local_map_ptrs()
+            self.flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        else:
+            self.peers, self.row0, self.nrows = None, 0, self.ny
+            self.scales = list(range(self.ns))
+            self.maps = torch.empty(4 * self.ns * nxy, dtype=torch.float64, device=self.dev)
+            self.map_ptrs = [self.maps.data_ptr() + m * self.ns * nxy * 8 for m in range(4)]
+        self.out_rows = []
+        for q in range(self.world):
+            a, b = row_range(self.ny, self.world, q)
+            cj0, myl = C.c_int(), C.c_int()
+            _lib.check(_lib.lib.pfx_l2_fit_rows_shape(self.ny, a, b - a, self.nn, C.byref(cj0), C.byref(myl)))
+            self.out_rows.append(myl.value)
+        self.my = sum(self.out_rows)
+        mine = max(self.out_rows[self.rank] * self.mx, 1)
+        # fit outputs of this rank, one block: [map][row][x] (+ status as the last "map", stored as float64)
+        self.fit_out = torch.zeros((self.nmaps + 1) * mine, dtype=torch.float64, device=self.dev)
+        self.fit_status = torch.zeros(mine, dtype=torch.int32, device=self.dev)
+        self.mine = mine
+
+    # ---- steps -------------------------------------------------------------------------------------
+    def load(self, topo, grav, wd_f):
+        """rank 0: copy the inputs into the pipeline's device buffers (host tensors: pinned memory makes the
+        copies asynchronous).  topo / grav are (nx, ny) C order, wd_f is the water depth with x fastest."""
+        if self.rank == 0:
+            self.d_topo.copy_(topo.reshape(-1), non_blocking=True)
+            self.d_grav.copy_(grav.reshape(-1), non_blocking=True)
+            self.d_wd.copy_(wd_f.reshape(-1), non_blocking=True)
+
+    def run(self):
+        """One pass over the inputs currently in d_topo / d_grav / d_wd of rank 0; returns on rank 0 the
+        (nmaps + 1, my, mx) float64 tensor of result maps (the last one the status words), None elsewhere."""
+        self.run_transform()
+        return self.run_fit()
+
+    def _bind_stream(self):
+        stream = torch.cuda.current_stream(self.dev)
+        self.plan.set_stream(stream.cuda_stream)
+        return stream
+
+    def run_cwt_only(self):
+        """This rank's share of the transform alone (no collectives): what the per-kernel timers measure."""
+        self._bind_stream()
+        if self.world > 1:
+            self.peers.transform_scales(self.plan, self.d_topo.data_ptr(), self.d_grav.data_ptr(), self.scales)
+        else:
+            self._lib.check(self._lib.lib.pfx_wlet_admit_coh_dev(self.plan.handle, self.d_topo.data_ptr(),
+                                                                 self.d_grav.data_ptr(), 0, self.ns, *self.map_ptrs))
+
+    def run_transform(self):
+        """Steps 1-3: broadcast, scale-sharded transform into the row shards, stream-ordered barrier."""
+        if self.world > 1:
+            dist.broadcast(self.d_topo, 0, group=self.group)
+            dist.broadcast(self.d_grav, 0, group=self.group)
+            dist.broadcast(self.d_wd, 0, group=self.group)
+        self.run_cwt_only()
+        if self.world > 1:
+            stream_barrier(self.flag, self.group)
+
+    def run_fit(self):
+        """Steps 4-5: fit of this rank's rows, gather on rank 0."""
+        lib, C = self._lib.lib, self._C
+        stream = self._bind_stream()
+        if self.nrows > 0 and self.out_rows[self.rank] > 0:
+            o = [self.fit_out.data_ptr() + i * self.mine * 8 for i in range(self.nmaps)]
+            te, te_s, f, f_s = o[0], o[1], o[2], o[3]
+            al, al_s, chi2 = (o[4], o[5], o[6]) if self.alph else (None, None, o[4])
+            wd = self.d_wd.data_ptr() + self.row0 * self.nx * 8
+            self._lib.check(lib.pfx_l2_fit_rows_dev(
+                self.local, stream.cuda_stream, C.byref(self.conf), self.d_k.data_ptr(), self.ns, self.nx, self.ny,
+                self.row0, self.nrows, *self.map_ptrs, wd, None, None, None, self.nn, int(self.alph),
+                self._lib.ATYPES[self.atype], te, te_s, f, f_s, al, al_s, chi2, self.fit_status.data_ptr()))
+            self.fit_out[self.nmaps * self.mine:].copy_(self.fit_status)  # int32 -> float64, exact
+        if self.world > 1:
+            return gather_rows_to_root(self.fit_out, self.nmaps + 1, self.mx, self.out_rows, 0, self.group)
+        return self.fit_out.view(self.nmaps + 1, self.out_rows[0], self.mx)
+
+    def launches(self):
+        return self.plan.launch_count()
+
+    def close(self):
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
+        self.plan.close()

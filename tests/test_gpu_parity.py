@@ -531,3 +531,215 @@ def test_float32_outputs_are_the_float64_results_rounded_once(pf, engine):
     p32.estimate_grid(nn=6)  # the fit takes float32 maps like SciPy takes the reference's
     p64.estimate_grid(nn=6)
     assert np.allclose(p32.mean_Te_grid, p64.mean_Te_grid, atol=0.05)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Round 2: parity at the BASELINE sizes against the oracle itself (not against properties)
+# ---------------------------------------------------------------------------------------------------------
+def _bench_pair(cfgname):
+    """The exact synthetic pair and wavenumbers bench.py uses for a BASELINE configuration."""
+    import bench
+    cfg = bench.CONFIGS[cfgname]
+    topo, grav, k, k0 = bench.workload(cfg)
+    return cfg, topo, grav, k, k0
+
+
+@pytest.mark.parametrize("cfgname,scales", [("C2", [0, 10, 19]), ("C4", [4, 18])])
+def test_pruned_engine_matches_oracle_at_baseline_sizes(pf, ora, cfgname, scales):
+    """BASELINE configs[1] (1024^2 land Bouguer) on scales {0, 10, 19} and configs[3] (2048^2 ocean free-air,
+    wd > 0) on two scales: the default engine through the C ABI against ora64 on the very grids bench.py times.
+    Tolerance: per scale plane max|d|/max|ref| <= 1e-9 and element-wise rtol 1e-9 (tests/helpers.py)."""
+    from plateflex_b200 import _lib
+    from plateflex_b200.cpwt import fused
+    cfg, topo, grav, k, k0 = _bench_pair(cfgname)
+    _lib.clear_plans()
+    ks = k[scales]
+    got = fused.wlet_admit_coh(topo, grav, cfg["dx"], cfg["dy"], ks)
+    ref = ora.admit_coh_from_grids(topo, grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=os.cpu_count() or 1)
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), got, ref):
+        assert_maps_close(a, b, f"{cfgname} {name}")
+    _lib.clear_plans()
+
+
+@pytest.mark.parametrize("cfgname", ["C2", "C4"])
+def test_fit_matches_scipy_on_sampled_cells_of_the_baseline_maps(pf, ora, cfgname):
+    """>= 512 random cells of the admittance / coherence maps of BASELINE configs[1] (Te, F) and configs[3]
+    (ocean, free air, alpha fitted): the device fit of the whole grid against the reference's L2_estimate_cell
+    logic on SciPy TRF (oracle/l2fit.py).  Interior optima: |dTe| < 0.1 km, |dF| < 1e-3, |dalpha| < 1e-2,
+    chi2 rel 1e-4, std rel 1e-2; cells where SciPy sits on a bound are compared on chi2 only and counted."""
+    from oracle import l2fit
+    from plateflex_b200 import _lib, estimate
+    from plateflex_b200.cpwt import fused
+    from plateflex_b200.flex import conf_flex
+    cfg, topo, grav, k, k0 = _bench_pair(cfgname)
+    pf.set_conf_flex()
+    conf_flex.boug = 1 if cfg["boug"] else 0
+    rhoc = 2800. if cfg["ocean"] else 2700.
+    conf_flex.rhoc = rhoc
+    _lib.clear_plans()
+    maps = fused.wlet_admit_coh(topo, grav, cfg["dx"], cfg["dy"], k)
+    wd = -np.minimum(topo, 0.0)
+    alph = bool(cfg["alph"])
+    res = estimate.L2_estimate_grid(k, *maps, wd, nn=1, alph=alph, atype="joint")
+    rng = np.random.default_rng(2026)
+    nx, ny = topo.shape
+    cells = np.stack([rng.integers(0, nx - 1, 512), rng.integers(0, ny - 1, 512)], axis=1)
+    npar = 3 if alph else 2
+    interior = bound = 0
+    for i, j in cells:
+        conf = ora.FlexConf(boug=conf_flex.boug, rhoc=rhoc, wd=float(wd[i, j]))
+        r = l2fit.L2_estimate_cell(k, maps[0][i, j], maps[1][i, j], maps[2][i, j], maps[3][i, j], alph=alph,
+                                   atype="joint", conf=conf)
+        assert res["status"][i, j] == 1
+        gm = [res["mean_Te"][i, j], res["mean_F"][i, j]] + ([res["mean_a"][i, j]] if alph else [])
+        gs = [res["std_Te"][i, j], res["std_F"][i, j]] + ([res["std_a"][i, j]] if alph else [])
+        if _compare_fit(gm, gs, res["chi2"][i, j], r["mean"], r["std"], r["chi2"], npar):
+            interior += 1
+        else:
+            bound += 1
+    assert interior + bound == 512 and interior >= 256, (interior, bound)
+    pf.set_conf_flex()
+    _lib.clear_plans()
+
+
+@pytest.mark.parametrize("variant", ["static", "group"])
+@pytest.mark.parametrize("alph", [False, True])
+def test_fit_kernel_variants_match_the_default(pf, monkeypatch, variant, alph):
+    """PLATEFLEX_B200_FIT=static (one cell per thread; also the fallback when the work counter cannot be
+    allocated) and =group (8 lanes per cell) run the same TRF arithmetic per cell as the lane-persistent
+    default: golden cells must agree with it to rounding."""
+    from plateflex_b200 import estimate
+    z = np.load(os.path.join(GOLD, "l2fit_cells.npz"))
+    pf.set_conf_flex()
+    n, ns = z["adm"].shape
+
+    def lay(a):
+        m = np.ones((n + 1, 2, ns), order="F")
+        m[:n, 0, :] = a
+        return m
+
+    args = (z["k"], lay(z["adm"]), lay(z["eadm"]), lay(z["coh"]), lay(z["ecoh"]))
+    ref = estimate.L2_estimate_grid(*args, wd=np.zeros((n + 1, 2)), nn=1, alph=alph, atype="joint")
+    monkeypatch.setenv("PLATEFLEX_B200_FIT", variant)
+    got = estimate.L2_estimate_grid(*args, wd=np.zeros((n + 1, 2)), nn=1, alph=alph, atype="joint")
+    assert np.array_equal(got["status"], ref["status"])
+    for name in ["mean_Te", "mean_F", "chi2", "std_Te", "std_F"] + (["mean_a", "std_a"] if alph else []):
+        tol = dict(rtol=1e-12, atol=0) if variant == "static" else dict(rtol=1e-6, atol=1e-9)
+        assert np.allclose(got[name], ref[name], **tol), (variant, name)
+
+
+@pytest.mark.parametrize("nx,ny", [(8200, 12), (12, 8200)])
+def test_padded_axis_16384_matches_oracle(pf, ora, nx, ny):
+    """BASELINE configs[4] (8192^2) pads both axes to 16384 samples (eight parts per line).  The full grid is
+    beyond what the CPU oracle finishes in a test, so the 16384-sample axis is exercised on a ragged strip, once
+    per axis, against ora64; the full-size run itself is covered by bench.py --config C5 (no oracle)."""
+    from plateflex_b200 import _lib, classes
+    from plateflex_b200.cpwt import fused
+    _lib.clear_plans()
+    t = red_field(nx, ny, seed=5) * 500.0
+    g = 0.06 * t + red_field(nx, ny, seed=6) * 25.0
+    k = classes._lam2k(8192, 8192, 5.0, 5.0)[1][:20][[2, 11, 19]]
+    got = fused.wlet_admit_coh(t, g, 5.0, 5.0, k)
+    ref = ora.admit_coh_from_grids(t, g, 5.0, 5.0, k, k0=pf.cf_wt.k0, prec=64, nthreads=os.cpu_count() or 1)
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), got, ref):
+        assert_maps_close(a, b, name)
+    _lib.clear_plans()
+
+
+def test_project_keeps_maps_on_the_device_until_read(pf, ora):
+    """Project.wlet_admit_coh leaves the four maps on the GPU; estimate_grid fits them there; reading an
+    attribute copies it once; assigning one falls back to the host path with identical results."""
+    from plateflex_b200 import synthetic
+    pf.set_conf_cpwt()
+    pf.set_conf_flex()
+    nx, ny, dx, dy = 40, 36, 20.0, 20.0
+    topo, grav = synthetic.make_pair(nx, ny, dx, dy, seed=20240011, Te=25.0, F=0.4)
+
+    def project():
+        p = pf.Project(grids=[pf.TopoGrid(topo.copy(), dx, dy), pf.BougGrid(grav, dx, dy)])
+        p.init()
+        return p
+
+    a = project()
+    assert not hasattr(a, "wl_admit")
+    a.wlet_admit_coh()
+    assert a.__dict__["_dmaps"] is not None and a.__dict__["_host_wl_admit"] is None
+    a.estimate_grid(nn=4)  # device path: no map has crossed to the host yet
+    assert a.__dict__["_host_wl_admit"] is None
+    s = a.estimate_cell(cell=(4, 8), returned=True)  # one cell fetched from the device
+    assert a.__dict__["_host_wl_coh"] is None and s.loc["Te", "mean"] == a.mean_Te_grid[1, 2]
+    adm = a.wl_admit  # first read copies
+    assert adm.shape == (nx, ny, a.ns) and adm.flags.f_contiguous and a.wl_admit is adm
+    ref = ora.admit_coh_from_grids(a.grids[0].data, grav, dx, dy, a.k, k0=pf.cf_wt.k0)
+    for name, r in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), ref):
+        assert_maps_close(getattr(a, name), r, name)
+    b = project()
+    b.wlet_admit_coh()
+    b.wl_admit = b.wl_admit.copy()  # assignment drops the device copy: host path from here on
+    assert b.__dict__["_dmaps"] is None
+    b.estimate_grid(nn=4)
+    for name in ("mean_Te_grid", "std_Te_grid", "mean_F_grid", "std_F_grid", "chi2_grid", "status_grid"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+
+
+def _ipc_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import bench
+        import plateflex_b200 as pf
+        from plateflex_b200 import sharding
+        pf.set_conf_cpwt()
+        pf.set_conf_flex()
+        cfg = dict(bench.CONFIGS["C1"], nx=96, ny=70, ns=9)
+        topo, grav, k, k0 = bench.workload(cfg)
+        conf = bench.flex_conf(cfg)
+        wd_f = np.ascontiguousarray((-np.minimum(topo, 0.0)).T)
+        pipe = sharding.TeMapPipeline(cfg["nx"], cfg["ny"], cfg["dx"], cfg["dy"], k, k0, conf, local_device=rank)
+        if rank == 0:
+            pipe.load(torch.from_numpy(topo), torch.from_numpy(grav), torch.from_numpy(wd_f))
+        got = pipe.run()
+        got2 = pipe.run()  # a second step reuses the shards: the broadcast orders it behind the first gather
+        torch.cuda.synchronize()
+        ok = True
+        if rank == 0:
+            solo = sharding.TeMapPipeline(cfg["nx"], cfg["ny"], cfg["dx"], cfg["dy"], k, k0, conf, local_device=0, solo=True)
+            solo.load(torch.from_numpy(topo), torch.from_numpy(grav), torch.from_numpy(wd_f))
+            ref = solo.run()
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref))) and bool(torch.equal(got, got2) or
+                     torch.equal(torch.nan_to_num(got), torch.nan_to_num(got2)))
+            ok = ok and float(ref[0].abs().max().item()) > 0
+            solo.close()
+        pipe.close()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_pipeline_equals_single_gpu_bit_for_bit(pf):
+    """Two processes, two GPUs: scale-sharded transform with the epilogue storing into the peer's row shard
+    through a CUDA-IPC mapping, stream-ordered barrier, row-sharded fit, gather -- the maps on rank 0 must be
+    bit-identical to the single-GPU maps.  Skipped on a one-GPU box (the driver's test box has one)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import socket
+
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

@@ -154,3 +154,28 @@ def test_filter_water_depth(pf):
     out = t.filter_water_depth(sigma=2, returned=True)
     assert out.shape == (30, 20) and (t.water_depth >= 0).all()
     assert (t.water_depth[t.data > 0] == 0).all() and (t.water_depth[t.data < -500] > 0).all()
+
+
+def test_project_maps_are_lazy_attributes(pf):
+    """wl_admit & co. behave like the reference's plain attributes (classes.py:968-971, probed with
+    try/except AttributeError at classes.py:1001-1008): absent before wlet_admit_coh, assignable, deletable."""
+    import numpy as np
+    topo = np.abs(np.random.default_rng(0).standard_normal((6, 5))) * 100. + 50.
+    proj = pf.Project(grids=[pf.TopoGrid(topo.copy(), 10., 10.), pf.BougGrid(topo * 0.1, 10., 10.)])
+    proj.init()
+    for name in ("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"):
+        assert not hasattr(proj, name)
+        try:
+            getattr(proj, name)
+            raise AssertionError("expected AttributeError")
+        except AttributeError as exc:
+            assert name in str(exc)
+    a = np.ones((6, 5, proj.ns))
+    proj.wl_admit = a
+    assert proj.wl_admit is a and hasattr(proj, "wl_admit") and not hasattr(proj, "wl_coh")
+    del proj.wl_admit
+    assert not hasattr(proj, "wl_admit")
+    # two projects do not share state through the class-level properties
+    other = pf.Project(grids=[pf.TopoGrid(topo.copy(), 10., 10.), pf.BougGrid(topo * 0.1, 10., 10.)])
+    proj.ewl_coh = a
+    assert not hasattr(other, "ewl_coh")

@@ -220,3 +220,35 @@ def test_flex_model_against_the_formulas_of_flex_f90(ora, te, f, alpha, wd, boug
     gg = nu_h ** 2 + (nu_w * ff) ** 2 + 2 * nu_h * nu_w * ff * np.cos(alpha)
     assert np.allclose(adm, np.real(hg) / hh, rtol=1e-10, atol=1e-16)
     assert np.allclose(coh, np.real(hg / np.sqrt(hh) / np.sqrt(gg)) ** 2, rtol=1e-10, atol=1e-16)
+
+
+# ---- pin: an independent float32 restatement (tests/np32_ref.py) must agree BIT FOR BIT -------------------
+@pytest.mark.parametrize("shape", [(64, 64), (32, 128), (2, 8)])
+@pytest.mark.parametrize("isign", [1, -1])
+def test_ora32_fourn_bit_exact_against_independent_numpy_float32(ora, shape, isign):
+    """cpwt_sub.f90:522-594 written twice from the Fortran (C in oracle/, numpy float32 in tests/np32_ref.py):
+    same bit-reversal, same double-precision twiddle recurrence truncated with sngl() per butterfly, same
+    single-precision butterflies -- so every output bit must match."""
+    import np32_ref
+    rng = np.random.default_rng(5)
+    d = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    re, im = np32_ref.fourn2(d, isign)
+    o = ora.fourn2(d, isign, prec=32)
+    assert np.array_equal(o.real, re) and np.array_equal(o.imag, im)
+
+
+def test_ora32_admit_coh_and_jackknife_bit_exact_against_independent_numpy_float32(ora):
+    """cpwt.f90:330-361 + cpwt_sub.f90:298-366 (azimuth means, admittance, coherence, running-prefix jackknife
+    with its zero guard and NaN -> 0) restated in numpy float32: all four maps bit for bit, including a cell
+    whose topography coefficients are all zero (NaN admittance, zero errors)."""
+    import np32_ref
+    rng = np.random.default_rng(6)
+    shape = (64, 64, 11, 2)
+    w1 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    w2 = (0.3 * w1 + rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    w1[3, 4, :, 0] = 0
+    ref = np32_ref.admit_coh(w1, w2)
+    got = ora.wlet_admit_coh(w1, w2, prec=32)
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), ref, got):
+        assert np.array_equal(a, b, equal_nan=True), name
+    assert np.isnan(got[0][3, 4, 0]) and got[1][3, 4, 0] == 0

@@ -60,6 +60,47 @@ def test_reshard_scale_blocks_to_row_blocks_gloo(world, nx, ny, ns):
     assert sorted(r for r, _ in res) == list(range(world)) and all(ok for _, ok in res)
 
 
+def _gather_worker(rank, world, port, nmaps, mx, out_rows, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from plateflex_b200 import sharding
+        rng = np.random.default_rng(11)
+        full = rng.standard_normal((nmaps, sum(out_rows), mx))
+        lo = sum(out_rows[:rank])
+        # the rank's block lives in a buffer that may be larger than what it owns (at least one element)
+        mine = np.zeros(max(nmaps * out_rows[rank] * mx, 1) + 3)
+        mine[:nmaps * out_rows[rank] * mx] = full[:, lo:lo + out_rows[rank], :].reshape(-1)
+        flag = torch.ones(1)
+        sharding.stream_barrier(flag)  # the stream-ordered barrier is a one-element all-reduce
+        got = sharding.gather_rows_to_root(torch.from_numpy(mine), nmaps, mx, out_rows, dst=0)
+        ok = float(flag.item()) == world
+        if rank == 0:
+            ok = ok and got.shape == full.shape and np.array_equal(got.numpy(), full)
+        else:
+            ok = ok and got is None
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nmaps,mx,out_rows", [(2, 6, 7, [4, 3]), (3, 8, 5, [2, 2, 0]), (2, 6, 1, [1, 1])])
+def test_gather_rows_to_root_gloo(world, nmaps, mx, out_rows):
+    """Result maps of the row shards (unequal, possibly empty) concatenated along y on rank 0 with one gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, nmaps, mx, out_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r for r, _ in res) == list(range(world)) and all(ok for _, ok in res)
+
+
 def test_partitions_cover_everything():
     from plateflex_b200 import sharding
     for n, world in [(20, 8), (20, 3), (3, 8), (1024, 8), (341, 4)]:
