@@ -251,6 +251,21 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
                         double *out_te_std, double *out_f, double *out_f_std, double *out_alpha, double *out_alpha_std,
                         double *out_chi2, int32_t *status);
 
+/* ---- the step in front of the path: grid ingest -------------------------- */
+/* GMT ".xyz" dumps as the reference's notebooks read them (docs/getting_started.rst:50-56, Ex1 cells 2-3): a
+ * first line "# name<TAB>xmin xmax ymin ymax zmin zmax dx dy nx ny" (gmt grdinfo -C) followed by one
+ * "x y z" line per node.  pfx_xyz_header returns those ten numbers; pfx_xyz_read parses the nvalues = nx*ny
+ * z values in file order (NaN accepted) with nthreads host threads (0 = automatic). */
+int pfx_xyz_header(const char *path, double *hdr10);
+int pfx_xyz_read(const char *path, long nvalues, double *z, int nthreads);
+/* Grid.__init__ (classes.py:143-153): every non-finite cell of the (nx, ny) C-order grid takes the value of
+ * the nearest finite cell (Euclidean distance in index units -- scipy.interpolate.griddata(method='nearest');
+ * equidistant candidates: smallest row, then smallest column).  In place; *nfilled (optional) = cells filled. */
+int pfx_nan_fill_nearest_host(int device, int nx, int ny, double *grid, long *nfilled);
+/* TopoGrid.filter_water_depth (classes.py:538-541): skimage.filters.gaussian(image, sigma) for a float image,
+ * i.e. scipy.ndimage.gaussian_filter(mode='nearest', truncate=4.0); (nx, ny) C order, in != out allowed. */
+int pfx_gaussian_filter_host(int device, int nx, int ny, double sigma, const double *in, double *out);
+
 #ifdef __cplusplus
 }
 #endif

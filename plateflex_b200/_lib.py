@@ -53,6 +53,10 @@ _SIGS = {
     "pfx_dev_free": ([_i, _vp], _i),
     "pfx_dev_h2d": ([_i, _vp, _vp, C.c_size_t], _i),
     "pfx_dev_d2h": ([_i, _vp, _vp, C.c_size_t], _i),
+    "pfx_xyz_header": ([C.c_char_p, _vp], _i),
+    "pfx_xyz_read": ([C.c_char_p, C.c_long, _vp, _i], _i),
+    "pfx_nan_fill_nearest_host": ([_i, _i, _i, _vp, C.POINTER(C.c_long)], _i),
+    "pfx_gaussian_filter_host": ([_i, _i, _i, _d, _vp, _vp], _i),
     "pfx_plan_create": ([C.POINTER(_vp), _i, _i, _d, _d, _vp, _i, _d, _i, _i], _i),
     "pfx_plan_destroy": ([_vp], _i),
     "pfx_plan_set_stream": ([_vp, _vp], _i),
