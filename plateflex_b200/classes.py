@@ -61,13 +61,13 @@ class Grid(object):
         self.ns, self.k = _lam2k(nx, ny, dx, dy)  # classes.py:141
 
         if np.any(np.isnan(np.array(grid))):
-            # nearest-neighbour fill of NaNs, classes.py:143-153 (host side, outside the hot path)
+            # nearest-neighbour fill of NaNs, classes.py:143-153: scipy.interpolate.griddata(method='nearest')
+            # in the reference, an exact nearest-finite-cell search on the GPU here (io.fill_nan_nearest).  Where
+            # two finite cells are exactly equidistant SciPy's pick depends on its k-d tree; ours is the
+            # smallest (row, column).
             print('grid contains NaN values. Performing interpolation...')
-            from scipy.interpolate import griddata
-            good = np.where(np.isfinite(grid))
-            xx, yy = np.mgrid[0:nx, 0:ny]
-            points = np.array([xx[good], yy[good]]).T
-            self.data = np.array(griddata(points, grid[good], (xx, yy), method='nearest'))
+            from . import io
+            self.data = io.fill_nan_nearest(np.array(grid, dtype=np.float64))
         else:
             self.data = np.array(grid)
 
@@ -155,8 +155,9 @@ class TopoGrid(Grid):
         self.water_depth = -1. * water_depth
 
     def filter_water_depth(self, sigma=10, returned=False):
-        """classes.py:538-546 (host side)."""
-        water_depth = _gaussian(self.data, sigma=sigma)
+        """classes.py:538-546; the Gaussian (skimage.filters.gaussian in the reference) runs on the GPU."""
+        from . import io
+        water_depth = io.gaussian_filter(self.data, sigma)
         water_depth[self.data > 0.] = 0.
         self.water_depth = -1. * water_depth
         if returned:

@@ -460,10 +460,16 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     const int is_base = is0;
     const int ngrids = g2 ? 2 : 1;
     const size_t nxy = (size_t)pl->nx * pl->ny;
-    PFX_CHECK(forward_spectrum(pl, g1, 0));
-    if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
+    {
+        NvtxRange r("pfx:forward");
+        PFX_CHECK(forward_spectrum(pl, g1, 0));
+        if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
+    }
     const bool pruned = pl->engine == PFX_ENGINE_PRUNED;
-    if (pruned) PFX_CHECK(pruned_prepare(pl, ngrids));
+    if (pruned) {
+        NvtxRange r("pfx:prepare");
+        PFX_CHECK(pruned_prepare(pl, ngrids));
+    }
     // With two plane buffers (pruned engine) the reduction of scale s overlaps the passes of scale s+1.
     const int nbuf = pruned ? pruned_num_buffers(pl) : 1;
     // Pageable host destinations (plain numpy arrays): every scale is enqueued first, then the finished
@@ -484,6 +490,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
         const int b = n & 1;
         const size_t so = (size_t)n * nxy;
         PlaneView v1, v2;
+        NvtxRange scale_range("pfx:scale", is, "");
         if (!pruned) {
             PFX_CHECK(dense_scale_planes(pl, is, ngrids));
             v1 = dense_view(pl, 0);
@@ -508,6 +515,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
             double *o[4] = {nullptr, nullptr, nullptr, nullptr};
             for (int i = 0; i < nouts && d_outs && !d32; i++) o[i] = d_outs[i] + so * elems[i];
             for (int i = 0; i < nouts && d32; i++) o[i] = reinterpret_cast<double *>(d32[i] + so * elems[i]);
+            NvtxRange r("pfx:reduce");
             ProfScope prof(pl, PFX_KC_REDUCE, red_stream);
             ShardOut sh;
             if (shards) {

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cufft.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -12,6 +13,21 @@
 namespace pfx {
 
 void set_error(const char *fmt, ...);
+
+// NVTX range around the host-side enqueue of one stage (header-only NVTX 3: a no-op unless a profiler injects
+// its library).  Stage names: pfx:forward, pfx:prepare, pfx:scale<is>:passes, pfx:scale<is>:reduce, pfx:l2_fit, ...
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    NvtxRange(const char *prefix, int n, const char *suffix)
+    {
+        char buf[64];
+        snprintf(buf, sizeof buf, "%s%d%s", prefix, n, suffix);
+        nvtxRangePushA(buf);
+    }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define PFX_CUDA(call)                                                                              \
     do {                                                                                            \

@@ -499,6 +499,7 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     const int ntr = PFX_NA * ngrids;
     const char *ctas_env = getenv("PLATEFLEX_B200_CTAS");
     {
+        NvtxRange r("pfx:pass1");
         ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
         if (st->v3y_nbuf[is]) {
             const int multi = (st->v2y[is] >> 5) & 1;
@@ -518,6 +519,7 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
         }
     }
     {
+        NvtxRange r("pfx:pass2");
         ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
         if (st->v3x_nbuf[is]) {
             const int multi = (st->v2x[is] >> 5) & 1;

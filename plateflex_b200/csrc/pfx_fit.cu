@@ -1282,6 +1282,7 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
                         double *out_chi2, int32_t *status)
 {
     const int ny = nrows;
+    NvtxRange nvtx_range("pfx:l2_fit");
     PFX_ARG(ny_total >= 1 && row0 >= 0 && nrows >= 1 && row0 + nrows <= ny_total, "bad row range");
     PFX_ARG(conf && k_dev, "conf or k is null");
     PFX_ARG(ns >= 1 && ns <= 64, "ns must be in [1, 64]");

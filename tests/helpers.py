@@ -10,10 +10,7 @@ ATOL_REL = 1e-12
 TE_TOL, F_TOL, A_TOL, CHI2_RTOL, STD_RTOL = 0.1, 1e-3, 1e-2, 1e-4, 1e-2
 
 
-def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_rel=ATOL_REL, floor=None):
-    """floor (optional, same shape): an absolute rounding floor per element added to the element-wise bound --
-    used for the jackknife error maps at the BASELINE sizes, where the error is a spread of eleven nearly equal
-    numbers v (sqrt(sum (v - mean)^2)): its attainable absolute accuracy is a few ulp of |v|, not of the spread."""
+def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_rel=ATOL_REL):
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     assert np.array_equal(np.isnan(got), np.isnan(ref)), f"{name}: NaN pattern differs"
@@ -28,8 +25,7 @@ def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_re
             continue
         err = np.abs(g[ok] - r[ok])
         assert err.max() / mx <= plane_tol, f"{name}[..., {s}]: max|d|/max|ref| = {err.max() / mx:.3e}"
-        extra = floor[..., s][ok] if floor is not None else 0.0
-        assert np.all(err <= rtol * np.abs(r[ok]) + atol_rel * mx + extra), \
+        assert np.all(err <= rtol * np.abs(r[ok]) + atol_rel * mx), \
             f"{name}[..., {s}]: element-wise tolerance exceeded ({(err / (np.abs(r[ok]) + 1e-300)).max():.3e})"
 
 

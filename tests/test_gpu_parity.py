@@ -548,19 +548,29 @@ def _bench_pair(cfgname):
 def test_pruned_engine_matches_oracle_at_baseline_sizes(pf, ora, cfgname, scales):
     """BASELINE configs[1] (1024^2 land Bouguer) on scales {0, 10, 19} and configs[3] (2048^2 ocean free-air,
     wd > 0) on two scales: the default engine through the C ABI against ora64 on the very grids bench.py times.
-    Tolerance: per scale plane max|d|/max|ref| <= 1e-9 and element-wise rtol 1e-9 (tests/helpers.py)."""
+    Tolerance (tests/helpers.py): per scale plane max|d|/max|ref| <= 1e-9 over ALL cells, and element-wise rtol
+    1e-9 over the cells whose local wavelet power is above 1e-8 of the plane's maximum for both grids.  The
+    round-off of an FFT is relative to the plane, not to the cell: two correct transforms differ by ~1e-15 of the
+    plane's amplitude, so ratios formed in cells 1e-4 times weaker than the strongest one cannot agree to 1e-9 --
+    those cells (well under 1 % here, asserted) are held to the plane criterion only."""
     from plateflex_b200 import _lib
     from plateflex_b200.cpwt import fused
     cfg, topo, grav, k, k0 = _bench_pair(cfgname)
     _lib.clear_plans()
     ks = k[scales]
     got = fused.wlet_admit_coh(topo, grav, cfg["dx"], cfg["dy"], ks)
-    ref = ora.admit_coh_from_grids(topo, grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=os.cpu_count() or 1)
-    # the jackknife errors are spreads of eleven nearly equal means of ratios: where the spread is below ~1e-6 of
-    # the value, a relative 1e-9 of the spread is under the rounding of the values themselves (64 ulp allowed)
-    floors = {"ewl_admit": 64 * np.finfo(float).eps * np.abs(ref[0]), "ewl_coh": 64 * np.finfo(float).eps * np.abs(ref[2])}
+    nt = os.cpu_count() or 1
+    w1 = ora.wlet_transform(topo, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=nt)
+    w2 = ora.wlet_transform(grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=nt)
+    ref = ora.wlet_admit_coh(w1, w2, prec=64)
+    p1, p2 = (np.abs(w1) ** 2).mean(axis=2), (np.abs(w2) ** 2).mean(axis=2)
+    del w1, w2
+    strong = (p1 >= 1e-8 * p1.max(axis=(0, 1))) & (p2 >= 1e-8 * p2.max(axis=(0, 1)))
+    assert strong.mean() > 0.99
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), got, ref):
-        assert_maps_close(a, b, f"{cfgname} {name}", floor=floors.get(name))
+        assert_maps_close(a, b, f"{cfgname} {name}", rtol=np.inf)  # plane criterion, every cell
+        assert_maps_close(np.where(strong, a, 0.0), np.where(strong, b, 0.0), f"{cfgname} {name} (cells above 1e-4 of the "
+                          "plane amplitude)")
     _lib.clear_plans()
 
 
@@ -767,3 +777,46 @@ def test_third_generation_pass_kernels_match_oracle(pf, ora, monkeypatch, knobs,
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), fused.wlet_admit_coh(t, g, dx, dy, kf), ref):
         assert_maps_close(a, b, name)
     _lib.clear_plans()
+
+
+def test_nan_fill_and_gaussian_match_scipy(pf):
+    """SURVEY.md 8f row 2 on the GPU: Grid.__init__'s nearest-neighbour NaN fill (classes.py:143-153) against
+    scipy.interpolate.griddata(method='nearest') -- every filled value must come from a finite cell at the minimal
+    distance, and equal SciPy's wherever that cell is unique -- and TopoGrid.filter_water_depth's Gaussian
+    (classes.py:538-541) against scipy.ndimage.gaussian_filter(mode='nearest', truncate=4), 1e-12 relative."""
+    from scipy import ndimage
+    from scipy.interpolate import griddata
+    from plateflex_b200 import io
+    rng = np.random.default_rng(12)
+    nx, ny = 61, 47
+    g = rng.standard_normal((nx, ny))
+    holes = g.copy()
+    holes[rng.random((nx, ny)) < 0.08] = np.nan
+    holes[:9, :7] = np.nan      # a corner block, as outside a map projection
+    holes[30:38, 20:31] = np.nan
+    got = io.fill_nan_nearest(holes)
+    good = np.where(np.isfinite(holes))
+    xx, yy = np.mgrid[0:nx, 0:ny]
+    ref = griddata(np.array([xx[good], yy[good]]).T, holes[good], (xx, yy), method='nearest')
+    assert np.isfinite(got).all() and np.array_equal(got[good], holes[good])
+    gi, gj = good
+    unique = same = 0
+    for i, j in zip(*np.where(~np.isfinite(holes))):
+        d2 = (gi - i) ** 2 + (gj - j) ** 2
+        near = np.where(d2 == d2.min())[0]
+        assert got[i, j] in holes[gi[near], gj[near]]
+        if len(near) == 1:
+            unique += 1
+            same += got[i, j] == ref[i, j]
+    assert unique > 50 and same == unique
+    grid = pf.Grid(holes, 10., 10.)  # the class uses it
+    assert np.array_equal(grid.data, got)
+    for sigma in (1, 2.5, 10):
+        out = io.gaussian_filter(g * 1000. - 2000., sigma)
+        want = ndimage.gaussian_filter(g * 1000. - 2000., sigma, mode='nearest', truncate=4.0)
+        assert np.abs(out - want).max() <= 1e-12 * np.abs(want).max()
+    topo = pf.TopoGrid(g * 1000. - 200., 10., 10.)
+    wd = topo.filter_water_depth(sigma=3, returned=True)
+    want = ndimage.gaussian_filter(topo.data, 3, mode='nearest', truncate=4.0)
+    want[topo.data > 0.] = 0.
+    assert np.allclose(wd, want, rtol=1e-12, atol=1e-9) and np.array_equal(topo.water_depth, -1. * wd)

@@ -61,7 +61,9 @@ def test_grid_attributes_and_unit_scaling(pf):
     assert isinstance(pf.BougGrid(data, 1, 1), pf.GravGrid) and pf.FairGrid(data, 1, 1).title == "Free-air anomaly"
 
 
+@pytest.mark.gpu
 def test_nan_fill(pf, capsys):
+    """The fill runs on the GPU (io.fill_nan_nearest); without a device the call fails loudly, no CPU fallback."""
     data = np.arange(12.0).reshape(3, 4)
     data[1, 1] = np.nan
     g = pf.Grid(data, 1.0, 1.0)
@@ -148,6 +150,7 @@ def test_save_results_writes_the_reference_csv_layout(pf, tmp_path, capsys):
         proj.save_results(MAP_Te=True, prefix=prefix)  # exists only after a Bayesian estimation
 
 
+@pytest.mark.gpu
 def test_filter_water_depth(pf):
     topo = np.linspace(-3000.0, 800.0, 30 * 20).reshape(30, 20)
     t = pf.TopoGrid(topo.copy(), 10.0, 10.0)
@@ -179,3 +182,38 @@ def test_project_maps_are_lazy_attributes(pf):
     other = pf.Project(grids=[pf.TopoGrid(topo.copy(), 10., 10.), pf.BougGrid(topo * 0.1, 10., 10.)])
     proj.ewl_coh = a
     assert not hasattr(other, "ewl_coh")
+
+
+def test_read_xyz_matches_the_notebooks_pandas_recipe(pf, tmp_path):
+    """Ex1_making_grids.ipynb cells 2-3: header fields from the first line, z column reshaped (ny, nx)[::-1]."""
+    import numpy as np
+    import pandas as pd
+    from plateflex_b200 import io
+    nx, ny = 37, 23
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal(nx * ny) * 1000.
+    z[[5, 99]] = np.nan
+    p = str(tmp_path / "Topo_NA.xyz")
+    with open(p, "w") as f:
+        f.write("# Topo_NA.grd\t-3380.0\t%g\t-3400.5\t%g\t-5300.5\t4200.25\t20.0169157785\t19.9970844654\t%d\t%d\n"
+                % (3440.0, 3380.0, nx, ny))
+        c = 0
+        for j in range(ny):
+            for i in range(nx):
+                f.write("%.4f\t%.4f\t%s\n" % (i * 20.0169, (ny - 1 - j) * 19.997, "NaN" if np.isnan(z[c]) else "%.3f" % z[c]))
+                c += 1
+    xmin, xmax, ymin, ymax, zmin, zmax, dx, dy, nnx, nny = \
+        pd.read_csv(p, sep='\t', nrows=0).columns[1:].values.astype(float)
+    want = pd.read_csv(p, sep='\t', skiprows=1, names=['x', 'y', 'z'])['z'].values.reshape(int(nny), int(nnx))[::-1]
+    data, gdx, gdy, h = io.read_xyz(p)
+    assert (gdx, gdy, h["nx"], h["ny"]) == (dx, dy, nx, ny) and h["xmin"] == xmin and h["zmax"] == zmax
+    assert data.shape == (ny, nx) and data.flags.c_contiguous and np.array_equal(data, want, equal_nan=True)
+    assert np.array_equal(io.read_xyz(p, nthreads=3)[0], want, equal_nan=True)
+    # errors: missing header, wrong count
+    bad = str(tmp_path / "bad.xyz")
+    open(bad, "w").write("0 0 1\n")
+    try:
+        io.read_xyz(bad)
+        raise AssertionError("expected ValueError")
+    except ValueError:
+        pass
