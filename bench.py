@@ -515,18 +515,29 @@ def _single_pipeline(sharding, nx, ny, cfg, k, k0, conf, local, engine):
                                   local_device=local, engine=engine, solo=True)
 
 
-def fit_roofline(fit_ms, cells, alph):
-    """FP64 roofline of the fit kernel: flops per cell counted by ncu on this workload (profiles/fit_flops.json,
-    scripts/summarise_ncu.py: 2*dfma + dadd + dmul thread instructions / fitted cells) against the DFMA peak
-    measured on this pool's B200 by scripts/fp64_peak.py (profiles/fp64_peak.json)."""
-    pk = profile_json("fp64_peak.json")
+def fp64_peak(local):
+    """Measured FP64 peak of this GPU (pfx_fp64_peak: independent DFMA chains on every SM), TFLOP/s; the committed
+    measurement of scripts/fp64_peak.py when the live one fails."""
+    try:
+        from plateflex_b200 import _lib
+        return max(_lib.fp64_peak(local) for _ in range(2)), "measured in this run (pfx_fp64_peak: DFMA chains, CUDA events)"
+    except Exception:  # noqa: BLE001
+        pk = profile_json("fp64_peak.json")
+        return (pk.get("tflops"), "profiles/fp64_peak.json") if pk else (None, None)
+
+
+def fit_roofline(fit_ms, cells, alph, peak, peak_src):
+    """FP64 roofline of the fit: flops per cell counted by ncu on this workload (profiles/fit_flops.json,
+    scripts/summarise_ncu.py: 2*dfma + dadd + dmul thread instructions / fitted cells) against the measured DFMA
+    peak."""
     fl = profile_json("fit_flops.json").get("alph" if alph else "noalph")
-    if not pk or not fl:
+    if not peak or not fl:
         return None
     achieved = fl["flops_per_cell"] * cells / (fit_ms * 1e-3) / 1e12
-    return {"bound": "fp64", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-            "flops_per_cell": fl["flops_per_cell"], "peak_source": "scripts/fp64_peak.py on B200 (profiles/fp64_peak.json)",
-            "flops_source": "ncu smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on (profiles/fit_flops.json)"}
+    return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "flops_per_cell": fl["flops_per_cell"], "fp64_pipe_pct": fl.get("fp64_pipe_pct"), "peak_source": peak_src,
+            "flops_source": "ncu smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on on " + fl.get("config", "?") +
+                            " (profiles/fit_flops.json)"}
 
 
 def main():
@@ -576,6 +587,7 @@ def main():
     nx, ny, ns = cfg["nx"], cfg["ny"], cfg["ns"]
     nxy = nx * ny
     peak, peak_src = measured_peak()
+    f64_peak, f64_src = fp64_peak(local)
     alg_total, alg = alg_bytes_per_unit(cfg)
     kern = r["kernels"]
     dom = max((c for c in kern if c in alg), key=lambda c: kern[c]["ms_per_step"], default=None)
@@ -585,11 +597,17 @@ def main():
         avg_s = kern[dom]["avg_launch_us"] * 1e-6
         achieved = alg[dom] * units_launch / avg_s / 1e9
         traffic = ncu_traffic(args.config, dom)
-        fp64 = profile_json("traffic.json").get(args.config + "_detail", {}).get(dom, {}).get("fp64_pipe_pct")
+        det = profile_json("traffic.json").get(args.config + "_detail", {}).get(dom, {})
+        fp64 = det.get("fp64_pipe_pct")
+        fl = det.get("fp64_flops_per_launch")
         step_s = r["stages"]["transform_ms"] * 1e-3
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "own_bytes_frac": (traffic / avg_s / 1e9 / peak) if traffic else None, "fp64_pipe_pct": fp64,
+                "fp64": ({"achieved": fl / avg_s / 1e12, "peak": f64_peak, "unit": "TFLOP/s", "frac": fl / avg_s / 1e12 / f64_peak,
+                          "flops_per_launch": fl, "peak_source": f64_src,
+                          "flops_source": "ncu 2*dfma + dadd + dmul thread instructions per launch (profiles/traffic.json)"}
+                         if (fl and f64_peak) else None),
                 "algorithmic_bytes_per_launch": alg[dom] * units_launch, "avg_launch_us": avg_s * 1e6,
                 "share_of_cwt": kern[dom]["ms_per_step"] / r["prof_ms"], "serialised_cwt_ms": r["prof_ms"],
                 "whole_transform": {"achieved": alg_total * r["units_job"] / step_s / 1e9,
@@ -617,7 +635,7 @@ def main():
     fit = dict(r.get("fit_stats") or {})
     fit.update({"ms": r["stages"]["fit_ms"], "cells_per_s": r["stages"]["fit_cells_per_s"], "atype": "joint",
                 "alph": bool(cfg["alph"]), "includes": "gather of the maps on rank 0" if sharded else "fit kernel only",
-                "roofline": fit_roofline(r["stages"]["fit_ms"], cells, cfg["alph"]) if world == 1 else None,
+                "roofline": fit_roofline(r["stages"]["fit_ms"], cells, cfg["alph"], f64_peak, f64_src) if world == 1 else None,
                 "cpu_baseline": fit_cpu})
     line = {
         "metric": METRIC, "value": r["value"], "unit": "units/s", "n_gpus": world, "steps": args.steps,

@@ -210,6 +210,18 @@ int pfx_flex_xspec_host(int device, const pfx_flex_conf *conf, const double *k, 
                         const double *f, const double *alpha, const double *wd, double *admit, double *coh,
                         double *jac_admit, double *jac_coh);
 
+/* ---- helper routines that numpy.f2py also exports (last rows) ------------------ */
+/* flex.f90:74-169 on ns-vectors: op 0 flexfilter_top(psi) -> o0; 1 flexfilter_bot(psi) -> o0; 2 decon(theta =
+ * in0, phi = in1, k = in2, A = p0) -> mu_h, mu_w, nu_h, nu_w; 3 tr_func(mu_h, mu_w, nu_h, nu_w, F = p0, alpha = p1)
+ * -> Re admit, Im admit, coh.  rhof and wd are the conf_flex module values (flex.f90:47-48). */
+int pfx_flex_helper_host(int device, const pfx_flex_conf *conf, double rhof, double wd, int op, int ns, const double *in0,
+                         const double *in1, const double *in2, const double *in3, double p0, double p1, double *o0,
+                         double *o1, double *o2, double *o3);
+/* cpwt_sub.f90:41-62 (defk) and :73-99 (wave_function, (nx, ny) complex, x fastest) in float64. */
+int pfx_defk_host(int device, int nx, int ny, double dx, double dy, double *kx, double *ky);
+int pfx_wave_function_host(int device, int nx, int ny, const double *kx, const double *ky, double k0, double scale,
+                           double angle, double *wave);
+
 /* ---- per-cell L2 fit: estimate.L2_estimate_cell over a grid ------------ */
 /* Replaces the Python loop of Project.estimate_grid (classes.py:1218-1304)
  * and the SciPy call of estimate.py:274-280 (+5 siblings).

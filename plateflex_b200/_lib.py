@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplateflex_b200.so")
+# PLATEFLEX_B200_LIB: another build of the library (kernel experiments: scripts/exp_build.sh)
+LIB_PATH = os.environ.get("PLATEFLEX_B200_LIB") or os.path.join(_HERE, "libplateflex_b200.so")
 
 NA = 11
 ENGINE_PRUNED, ENGINE_DENSE = 0, 1
@@ -88,6 +89,9 @@ _SIGS = {
     "pfx_cube_xscalogram_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp], _i),
     "pfx_cube_admit_coh_host": ([_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "pfx_flex_xspec_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "pfx_flex_helper_host": ([_i, C.POINTER(FlexConf), _d, _d, _i, _i, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp], _i),
+    "pfx_defk_host": ([_i, _i, _i, _d, _d, _vp, _vp], _i),
+    "pfx_wave_function_host": ([_i, _i, _i, _vp, _vp, _d, _d, _d, _vp], _i),
     "pfx_l2_fit_host": ([_i, C.POINTER(FlexConf), _vp, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] + [_vp] * 8, _i),
     "pfx_l2_fit_rows_shape": ([_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)], _i),
     "pfx_l2_fit_rows_dev": ([_i, _vp, C.POINTER(FlexConf), _vp, _i, _i, _i, _i, _i] + [_vp] * 8 + [_i, _i, _i] +

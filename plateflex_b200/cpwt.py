@@ -127,6 +127,28 @@ class _Cpwt:
         return tuple(outs)
 
 
+    # -- helper subroutines of cpwt_sub.f90 that f2py exports at module level (unused by the package)
+    def npow2(self, n):
+        """cpwt_sub.f90:26-33."""
+        return int(_lib.lib.pfx_npow2(int(n)))
+
+    def defk(self, nx, ny, dx, dy):
+        """cpwt_sub.f90:41-62 -> (kx, ky), float64, positive Nyquist."""
+        kx, ky = np.empty(int(nx)), np.empty(int(ny))
+        _lib.check(_lib.lib.pfx_defk_host(_lib.default_device(), int(nx), int(ny), float(dx), float(dy), _lib.ptr(kx),
+                                          _lib.ptr(ky)))
+        return kx, ky
+
+    def wave_function(self, kx, ky, k0, scales, angle):
+        """cpwt_sub.f90:73-99 -> daughter wavelet (nx, ny) complex128, Fortran order."""
+        kx = np.ascontiguousarray(kx, dtype=np.float64).ravel()
+        ky = np.ascontiguousarray(ky, dtype=np.float64).ravel()
+        out = np.empty((len(kx), len(ky)), dtype=np.complex128, order="F")
+        _lib.check(_lib.lib.pfx_wave_function_host(_lib.default_device(), len(kx), len(ky), _lib.ptr(kx), _lib.ptr(ky),
+                                                   float(k0), float(scales), float(angle), _lib.ptr(out)))
+        return out
+
+
 cpwt = _Cpwt()
 
 

@@ -162,6 +162,8 @@ struct PrunedState {
     std::vector<int> v2x, v2y, v2x_ctas, v2y_ctas;
     // third-generation pass 2 (pfx_pruned_v3.cuh): line buffers in the ring (0 = not used for this scale)
     std::vector<int> v3x_nbuf, v3x_ctas, v3y_nbuf, v3y_ctas;
+    // 128-thread form of the second-generation pass 2 (namespace v2h): CTAs resident per SM, 0 = not used
+    std::vector<int> v2hx_ctas;
     int v3_occ = 3;  // CTAs per SM the v3 kernels are compiled for (PLATEFLEX_B200_V3_OCC = 2 | 3)
     int nsm = 148;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
@@ -218,6 +220,10 @@ int plan_init_pruned(pfx_plan *pl)
     st->v3x_ctas.assign(ns, 0);
     st->v3y_nbuf.assign(ns, 0);
     st->v3y_ctas.assign(ns, 0);
+    st->v2hx_ctas.assign(ns, 0);
+    // PLATEFLEX_B200_V2H = "on": pass 2 with 128-thread CTAs (parts of 1024 elements) where the FFT length allows
+    const char *v2h_env = getenv("PLATEFLEX_B200_V2H");
+    const bool v2h_on = v2h_env && !strcmp(v2h_env, "on");
     // PLATEFLEX_B200_V3 = "on" | "1" | "2" (ring depth): third-generation pass kernels with bulk-copy staged support
     // samples.  Opt-in: they need the intermediate transposed, and the scattered stores that costs pass 1 outweigh
     // what pass 2 gains on B200 (measured, profiles/README.md), so the second generation stays the default.
@@ -402,7 +408,10 @@ int plan_init_pruned(pfx_plan *pl)
         } else {
             PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
         }
-        if (st->v3x_nbuf[is]) {
+        if (v2h_on && !st->v3x_nbuf[is] && st->v2x[is] >= 0 && sd.ax.logL <= 10) {
+            PFX_CHECK(v2h_configure_p2(sd.ax.logL, sd.ax.N > 1024, &res));
+            st->v2hx_ctas[is] = std::max(res, 1) * st->nsm;
+        } else if (st->v3x_nbuf[is]) {
             // two line buffers when three CTAs per SM still fit, else one (refilled behind the first stage)
             const int multi = (st->v2x[is] >> 5) & 1, half = 2 * nx == NX;
             int nbuf = v3_depth ? v3_depth : 2;
@@ -527,6 +536,10 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
             // every transform has the same number of rows: one wave of persistent CTAs
             const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v3x_ctas[is] / ntr);
             PFX_CHECK(v3_launch_p2(va, sd.ax.logL, multi, 2 * pl->nx == pl->NX, st->v3_occ, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+        } else if (st->v2hx_ctas[is]) {
+            v2h::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 10, 1)};
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v2hx_ctas[is] / ntr);
+            PFX_CHECK(v2h_launch_p2(va, sd.ax.logL, sd.ax.N > 1024, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
         } else if (st->v2x[is] >= 0) {
             v2::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
             const int cpc = st->v2x[is] & 15, groups = (pl->ny + cpc - 1) / cpc;

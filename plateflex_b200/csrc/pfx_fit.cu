@@ -53,6 +53,15 @@ struct FitArgs {
     int32_t *status;
     unsigned long long *counter;  // lane-persistent kernel: next cell to hand out (zeroed before the launch)
     int fetch_min;                // ... lanes of a warp wait until this many of them need a new cell
+    // Tail control: once the work counter has run out, a lane gives up a cell that has not terminated after
+    // trial_cap model evaluations and appends it to todo[] (todo_count, zeroed before the launch; cells beyond
+    // todo_cap stay with their lane); the finisher -- the 8-lanes-per-cell kernel, a fraction of the latency per
+    // trial -- then fits exactly those cells from the start.  A cell that needs hundreds of trials no longer
+    // holds the whole grid for milliseconds at the end; while fresh cells remain nothing is handed over.
+    int *todo = nullptr;
+    unsigned long long *todo_count = nullptr;
+    int todo_cap = 0, trial_cap = 0;
+    int finisher = 0;  // fit_kernel: take the cells from todo[0 .. min(*todo_count, todo_cap))
 };
 
 template <int NP>
@@ -781,6 +790,7 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
     // ---- per-lane state of the cell in flight
     bool have = false, more = true, init = false;
     size_t dst = 0;
+    int mycell = 0;
     FlexCell fc = flex_cell(a.conf, a.conf.rhoc, a.conf.zc, 0.);
     double cdeep = 0., ctop = 0.;
     double x[NP];
@@ -854,6 +864,7 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
                 const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
                 const size_t src = (size_t)((a.cj0 + cj) * a.nn - a.row0) * a.nx + (size_t)ci * a.nn;
                 dst = (size_t)cj * a.mx + ci;
+                mycell = (int)cell;
                 if (!(a.mask && a.mask[src])) {  // classes.py:1228-1231 (outputs of masked cells stay zero)
                     const double rhoc = a.rhoc_map ? a.rhoc_map[src] : a.conf.rhoc;  // classes.py:1087-1091
                     const double zc = a.zc_map ? a.zc_map[src] : a.conf.zc;
@@ -910,7 +921,20 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
             for (int p = 0; p < NP; p++) g_norm = fmax(g_norm, fabs(cur.g[p] * v[p]));
             int status = -1;
             if (g_norm < TRF_GTOL) status = 1;
-            if (status != -1 || nfev >= TRF_MAX_NFEV) {
+            bool handed_over = false;
+            // only in the tail: while fresh cells remain, a long cell costs nothing but its own lane
+            if (status == -1 && a.todo && nfev >= a.trial_cap && nfev < TRF_MAX_NFEV && ((nfev - a.trial_cap) & 7) == 0 &&
+                *reinterpret_cast<volatile unsigned long long *>(a.counter) >= (unsigned long long)ncells) {
+                const unsigned long long slot = atomicAdd(a.todo_count, 1ull);
+                if (slot < (unsigned long long)a.todo_cap) {
+                    a.todo[slot] = mycell;
+                    handed_over = true;
+                }  // list full: the lane keeps the cell (the count is clamped by the finisher)
+            }
+            if (handed_over) {
+                have = false;
+                act = false;
+            } else if (status != -1 || nfev >= TRF_MAX_NFEV) {
                 write_cell<NP>(a, dst, m, x, cur, status, nfev);
                 have = false;
                 act = false;
@@ -1022,12 +1046,17 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
-    const long long ncells = (long long)a.fx * a.fy;
+    long long ncells = (long long)a.fx * a.fy;
+    if (a.finisher) {
+        const unsigned long long n = *a.todo_count;
+        ncells = (long long)(n < (unsigned long long)a.todo_cap ? n : (unsigned long long)a.todo_cap);
+    }
     const size_t nxy = (size_t)a.nx * a.ny;
     const bool use_adm = a.atype != PFX_ATYPE_COH, use_coh = a.atype != PFX_ATYPE_ADMIT;
     const int m = (use_adm ? a.ns : 0) + (use_coh ? a.ns : 0);
 
-    for (long long cell = group; cell < ncells; cell += ngroups) {
+    for (long long item = group; item < ncells; item += ngroups) {
+        const long long cell = a.finisher ? (long long)a.todo[item] : item;
         const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
         const int i = ci * a.nn, j = (a.cj0 + cj) * a.nn - a.row0;
         const size_t src = (size_t)j * a.nx + i;
@@ -1173,7 +1202,7 @@ __global__ void xspec_kernel(pfx_flex_conf conf, const double *__restrict__ k, i
 template <int G, int NSL>
 int launch_fit_np(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 {
-    const long long ncells = (long long)a.fx * a.fy;
+    const long long ncells = a.finisher ? (long long)a.todo_cap : (long long)a.fx * a.fy;
     const int threads = 128;
     long long blocks = (ncells * G + threads - 1) / threads;
     const long long cap = (long long)nsm * 16;
@@ -1227,26 +1256,34 @@ int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 
 using namespace pfx;
 
-// Work counters of the lane-persistent fit kernel: a small per-device ring of device words, one per
-// launch, zeroed on the launch stream.  A word comes round again after FIT_COUNTERS launches.
+// Per-call scratch of the lane-persistent fit kernel, allocated and freed in stream order (cudaMallocAsync): the
+// work counter, the count and the list of the cells handed to the finisher.  Nothing is shared between calls, so
+// concurrent fits on different streams cannot touch each other's counters.
 namespace {
-constexpr int FIT_COUNTERS = 64, FIT_MAX_DEVICES = 64;
-std::mutex g_counter_mutex;
-unsigned long long *g_counters[FIT_MAX_DEVICES] = {};
-unsigned g_counter_next[FIT_MAX_DEVICES] = {};
+struct FitScratch {
+    unsigned long long *words = nullptr;  // [0] work counter, [1] todo count
+    int *todo = nullptr;
+    int todo_cap = 0;
+};
 
-unsigned long long *next_fit_counter(int device)
+int fit_scratch_alloc(FitScratch &sc, long long ncells, cudaStream_t st)
 {
-    if (device < 0 || device >= FIT_MAX_DEVICES) return nullptr;
-    std::lock_guard<std::mutex> lock(g_counter_mutex);
-    if (!g_counters[device]) {
-        if (cudaMalloc(&g_counters[device], FIT_COUNTERS * sizeof(unsigned long long)) != cudaSuccess) {
-            cudaGetLastError();
-            g_counters[device] = nullptr;
-            return nullptr;
-        }
+    long long cap = ncells / 16 + 1024;  // cells that exceed the trial cap are well under 1 % of a grid
+    if (cap > ncells) cap = ncells;
+    if (cap < 1) cap = 1;
+    void *p = nullptr;
+    const size_t bytes = 16 + (size_t)cap * sizeof(int);
+    cudaError_t e = cudaMallocAsync(&p, bytes, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("fit scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PFX_ERR_OOM : PFX_ERR_CUDA;
     }
-    return g_counters[device] + (g_counter_next[device]++ % FIT_COUNTERS);
+    sc.words = static_cast<unsigned long long *>(p);
+    sc.todo = reinterpret_cast<int *>(sc.words + 2);
+    sc.todo_cap = (int)cap;
+    PFX_CUDA(cudaMemsetAsync(sc.words, 0, 16, st));
+    return PFX_OK;
 }
 }  // namespace
 
@@ -1331,7 +1368,7 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
     a.o_a_std = out_alpha_std;
     a.o_chi2 = out_chi2;
     a.status = status;
-    a.counter = next_fit_counter(device);
+    a.counter = nullptr;
     {
         const char *fb = getenv("PLATEFLEX_B200_FIT_BATCH");
         a.fetch_min = (fb && atoi(fb) >= 1 && atoi(fb) <= 32) ? atoi(fb) : 24;
@@ -1354,29 +1391,48 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
         zero(out_alpha_std, mo * 8);
     }
     zero(status, mo * 4);
-    zero(a.counter, sizeof(unsigned long long));
+    FitScratch scratch;
+    const char *mode = getenv("PLATEFLEX_B200_FIT");
+    const bool lanes_wanted = !(mode && (!strcmp(mode, "group") || !strcmp(mode, "static")));
+    if (rc == PFX_OK && a.fx > 0 && a.fy > 0 && lanes_wanted) {
+        rc = fit_scratch_alloc(scratch, (long long)a.fx * a.fy, st);
+        if (rc == PFX_OK) {
+            a.counter = scratch.words;
+            // PLATEFLEX_B200_FIT_CAP: model evaluations after which a lane hands its cell to the finisher (0: never)
+            const char *ce = getenv("PLATEFLEX_B200_FIT_CAP");
+            const int capv = ce ? atoi(ce) : 32;
+            if (capv > 0) {
+                a.todo = scratch.todo;
+                a.todo_count = scratch.words + 1;
+                a.todo_cap = scratch.todo_cap;
+                a.trial_cap = capv;
+            }
+        }
+    }
     if (rc == PFX_OK && a.fx > 0 && a.fy > 0) {
         // range(0, nx-nn, nn) never reaches index mx*nn or beyond (classes.py:1218 vs 1189)
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-        const char *mode = getenv("PLATEFLEX_B200_FIT");
-        if (mode && !strcmp(mode, "group")) {  // cooperative variant: 8 or 16 lanes per cell
-            if (ns <= 8)
-                rc = launch_fit_np<8, 1>(a, alph, st, nsm);
-            else if (ns <= 16)
-                rc = launch_fit_np<8, 2>(a, alph, st, nsm);
-            else if (ns <= 24)
-                rc = launch_fit_np<8, 3>(a, alph, st, nsm);
-            else if (ns <= 32)
-                rc = launch_fit_np<8, 4>(a, alph, st, nsm);
-            else if (ns <= 48)
-                rc = launch_fit_np<16, 3>(a, alph, st, nsm);
-            else
-                rc = launch_fit_np<16, 4>(a, alph, st, nsm);
+        auto group_fit = [&](const FitArgs &g) -> int {  // cooperative variant: 8 or 16 lanes per cell
+            if (ns <= 8) return launch_fit_np<8, 1>(g, alph, st, nsm);
+            if (ns <= 16) return launch_fit_np<8, 2>(g, alph, st, nsm);
+            if (ns <= 24) return launch_fit_np<8, 3>(g, alph, st, nsm);
+            if (ns <= 32) return launch_fit_np<8, 4>(g, alph, st, nsm);
+            if (ns <= 48) return launch_fit_np<16, 3>(g, alph, st, nsm);
+            return launch_fit_np<16, 4>(g, alph, st, nsm);
+        };
+        if (mode && !strcmp(mode, "group")) {
+            rc = group_fit(a);
         } else {
             rc = launch_fit_cell(a, alph, st, nsm);
+            if (rc == PFX_OK && a.counter && a.todo) {  // the cells the lanes gave up after trial_cap evaluations
+                FitArgs fin = a;
+                fin.finisher = 1;
+                rc = group_fit(fin);
+            }
         }
     }
+    if (scratch.words) cudaFreeAsync(scratch.words, st);
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return rc;
 }
@@ -1485,6 +1541,155 @@ int pfx_flex_xspec_host(int device, const pfx_flex_conf *conf, const double *k, 
     cudaFree(d);
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     return rc;
+}
+
+}  // extern "C"
+
+// ---- the helper routines numpy.f2py also exports from flex.f90 / cpwt_sub.f90 -------------------------------
+// flexfilter_top (flex.f90:74-86), flexfilter_bot (:94-106), decon (:115-132), tr_func (:141-169), defk
+// (cpwt_sub.f90:41-62) and wave_function (cpwt_sub.f90:73-99).  The package itself never calls them; they exist so
+// that a script using plateflex.flex.flex.decon(...) etc. keeps working.  Written as the Fortran writes them
+// (IEEE divisions, no fused reciprocals): these are convenience entry points, not the fit's inner loop.
+namespace pfx {
+namespace {
+
+enum { FH_TOP = 0, FH_BOT = 1, FH_DECON = 2, FH_TRFUNC = 3 };
+
+__global__ void flex_helper_kernel(int op, pfx_flex_conf c, double rhof, double wd, int ns, const double *in0,
+                                   const double *in1, const double *in2, const double *in3, double p0, double p1,
+                                   double *o0, double *o1, double *o2, double *o3)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= ns) return;
+    const double rcf = c.rhoc - rhof, drho = c.rhom - c.rhoc;
+    if (op == FH_TOP) {
+        o0[s] = -(rcf / drho) / (1. + in0[s] / drho / FLEX_G);
+    } else if (op == FH_BOT) {
+        o0[s] = -(rcf / drho) * (1. + in0[s] / rcf / FLEX_G);
+    } else if (op == FH_DECON) {  // in0 = theta, in1 = phi, in2 = k, p0 = A
+        const double theta = in0[s], phi = in1[s], k = in2[s];
+        o0[s] = 1. / (1. - theta);
+        o1[s] = 1. / (phi - 1.);
+        const double top = p0 * rcf * exp(-k * wd), deep = drho * exp(-k * (c.zc + wd));
+        o2[s] = 2. * FLEX_PI * FLEX_GC * (top + deep * theta) / (1. - theta);
+        o3[s] = 2. * FLEX_PI * FLEX_GC * (top + deep * phi) / (phi - 1.);
+    } else {  // tr_func: in0..3 = mu_h, mu_w, nu_h, nu_w; p0 = F, p1 = alpha -> o0/o1 = admit (re, im), o2 = coh
+        const double mu_h = in0[s], mu_w = in1[s], nu_h = in2[s], nu_w = in3[s];
+        const double r = rcf / drho, ff = p0 / (1. - p0), t = ff * r;
+        const double hgr = nu_h * mu_h + nu_w * mu_w * (ff * ff) * (r * r) + (nu_h * mu_w + nu_w * mu_h) * t * cos(p1);
+        const double hgi = (nu_h * mu_w - nu_w * mu_h) * t * sin(p1);
+        const double hh = mu_h * mu_h + (mu_w * t) * (mu_w * t) + 2. * mu_h * mu_w * t * cos(p1);
+        const double gg = nu_h * nu_h + (nu_w * t) * (nu_w * t) + 2. * nu_h * nu_w * t * cos(p1);
+        o0[s] = hgr / hh;
+        o1[s] = hgi / hh;
+        const double cr = hgr / sqrt(hh) / sqrt(gg);
+        o2[s] = cr * cr;
+    }
+}
+
+// cpwt_sub.f90:41-62 and :73-99 in float64; wave is (nx, ny) complex, x fastest (the Fortran layout)
+__global__ void defk_kernel(int n, double d, double *k)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dk = 2. * FLEX_PI / ((double)n * d);
+    k[i] = (i <= n / 2) ? (double)i * dk : -((double)(n - i) * dk);
+}
+
+__global__ void wave_function_kernel(int nx, int ny, const double *kx, const double *ky, double k0, double scale,
+                                     double angle, double2 *wave)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nx) return;
+    const double kx0 = k0 * cos(angle), ky0 = k0 * sin(angle), norm = scale / sqrt(FLEX_PI);
+    const double a = scale * kx[i] - kx0, b = scale * ky[j] - ky0;
+    const double main = exp(-0.5 * (a * a)) * exp(-0.5 * (b * b));
+    const double adm = exp(-0.5 * ((kx[i] * kx[i] + ky[j] * ky[j]) + (kx0 * kx0 + ky0 * ky0)));
+    wave[(size_t)j * nx + i] = make_double2(norm * (main - adm), 0.);
+}
+
+}  // namespace
+}  // namespace pfx
+
+extern "C" {
+
+int pfx_flex_helper_host(int device, const pfx_flex_conf *conf, double rhof, double wd, int op, int ns, const double *in0,
+                         const double *in1, const double *in2, const double *in3, double p0, double p1, double *o0,
+                         double *o1, double *o2, double *o3)
+{
+    PFX_ARG(conf && ns >= 1 && op >= 0 && op <= 3 && in0 && o0, "bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    double *d = nullptr;
+    PFX_CUDA(cudaMalloc(&d, (size_t)8 * ns * sizeof(double)));
+    const double *hin[4] = {in0, in1, in2, in3};
+    double *hout[4] = {o0, o1, o2, o3};
+    for (int q = 0; q < 4; q++)
+        if (hin[q]) cudaMemcpyAsync(d + (size_t)q * ns, hin[q], ns * sizeof(double), cudaMemcpyHostToDevice, 0);
+    flex_helper_kernel<<<(ns + 127) / 128, 128>>>(op, *conf, rhof, wd, ns, d, d + ns, d + 2 * (size_t)ns, d + 3 * (size_t)ns,
+                                                  p0, p1, d + 4 * (size_t)ns, d + 5 * (size_t)ns, d + 6 * (size_t)ns,
+                                                  d + 7 * (size_t)ns);
+    for (int q = 0; q < 4; q++)
+        if (hout[q]) cudaMemcpyAsync(hout[q], d + (size_t)(4 + q) * ns, ns * sizeof(double), cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        set_error("flex helper failed: %s", cudaGetErrorString(e));
+        return PFX_ERR_CUDA;
+    }
+    return PFX_OK;
+}
+
+int pfx_defk_host(int device, int nx, int ny, double dx, double dy, double *kx, double *ky)
+{
+    PFX_ARG(nx >= 1 && ny >= 1 && dx > 0 && dy > 0 && kx && ky, "bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    double *d = nullptr;
+    PFX_CUDA(cudaMalloc(&d, (size_t)(nx + ny) * sizeof(double)));
+    defk_kernel<<<(nx + 127) / 128, 128>>>(nx, dx, d);
+    defk_kernel<<<(ny + 127) / 128, 128>>>(ny, dy, d + nx);
+    cudaMemcpyAsync(kx, d, nx * sizeof(double), cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(ky, d + nx, ny * sizeof(double), cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        set_error("defk failed: %s", cudaGetErrorString(e));
+        return PFX_ERR_CUDA;
+    }
+    return PFX_OK;
+}
+
+int pfx_wave_function_host(int device, int nx, int ny, const double *kx, const double *ky, double k0, double scale,
+                           double angle, double *wave)
+{
+    PFX_ARG(nx >= 1 && ny >= 1 && kx && ky && wave, "bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) PFX_CUDA(cudaSetDevice(device));
+    double *d = nullptr;
+    const size_t n = (size_t)nx * ny;
+    PFX_CUDA(cudaMalloc(&d, (nx + ny + 2 + 2 * n) * sizeof(double)));
+    cudaMemcpyAsync(d, kx, nx * sizeof(double), cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(d + nx, ky, ny * sizeof(double), cudaMemcpyHostToDevice, 0);
+    double2 *w = reinterpret_cast<double2 *>(d + ((nx + ny + 1) & ~1));
+    wave_function_kernel<<<dim3((nx + 127) / 128, ny), 128>>>(nx, ny, d, d + nx, k0, scale, angle, w);
+    cudaMemcpyAsync(wave, w, n * sizeof(double2), cudaMemcpyDeviceToHost, 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d);
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        set_error("wave_function failed: %s", cudaGetErrorString(e));
+        return PFX_ERR_CUDA;
+    }
+    return PFX_OK;
 }
 
 }  // extern "C"

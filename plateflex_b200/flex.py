@@ -49,6 +49,37 @@ class _Flex:
         conf_flex.rhof = conf_flex.rhow if conf_flex.wd > 0.0 else conf_flex.rhoa
         return adm[0], coh[0]
 
+    # -- the helper subroutines f2py also exports (flex.f90:74-169); the package itself never calls them
+    def _helper(self, op, ins, p0=0.0, p1=0.0, nout=1):
+        ins = [np.ascontiguousarray(a, dtype=np.float64).ravel() for a in ins]
+        ns = len(ins[0])
+        if any(len(a) != ns for a in ins):
+            raise ValueError("input arrays must have the same length")
+        outs = [np.empty(ns) for _ in range(nout)]
+        conf = conf_flex.as_struct()
+        pin = [_lib.ptr(a) for a in ins] + [None] * (4 - len(ins))
+        pout = [_lib.ptr(a) for a in outs] + [None] * (4 - nout)
+        _lib.check(_lib.lib.pfx_flex_helper_host(_lib.default_device(), C.byref(conf), float(conf_flex.rhof),
+                                                 float(conf_flex.wd), op, ns, *pin, float(p0), float(p1), *pout))
+        return outs
+
+    def flexfilter_top(self, psi):
+        """flex.f90:74-86 (reads rhoc, rhom, rhof from conf_flex as the Fortran does)."""
+        return self._helper(0, [psi])[0]
+
+    def flexfilter_bot(self, psi):
+        """flex.f90:94-106."""
+        return self._helper(1, [psi])[0]
+
+    def decon(self, theta, phi, k, a):
+        """flex.f90:115-132 -> (mu_h, mu_w, nu_h, nu_w)."""
+        return tuple(self._helper(2, [theta, phi, k], p0=a, nout=4))
+
+    def tr_func(self, mu_h, mu_w, nu_h, nu_w, f, alpha):
+        """flex.f90:141-169 -> (admit complex128, coh)."""
+        re, im, coh = self._helper(3, [mu_h, mu_w, nu_h, nu_w], p0=f, p1=alpha, nout=3)
+        return re + 1j * im, coh
+
     def real_xspec_batch(self, k, te, f, alpha, wd=None, jac=False, device=None):
         """Many parameter sets at once: returns (admit, coh) of shape (ncurves, ns); with
         ``jac`` also the analytic d/d(Te, F, alpha) arrays of shape (ncurves, 3, ns)."""

@@ -10,7 +10,8 @@ ATOL_REL = 1e-12
 TE_TOL, F_TOL, A_TOL, CHI2_RTOL, STD_RTOL = 0.1, 1e-3, 1e-2, 1e-4, 1e-2
 
 
-def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_rel=ATOL_REL):
+def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_rel=ATOL_REL, elementwise=True, floor=None):
+    """floor (optional, same shape): an absolute accuracy floor per element added to the element-wise bound."""
     got, ref = np.asarray(got), np.asarray(ref)
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     assert np.array_equal(np.isnan(got), np.isnan(ref)), f"{name}: NaN pattern differs"
@@ -25,7 +26,8 @@ def assert_maps_close(got, ref, name="", plane_tol=PLANE_TOL, rtol=RTOL, atol_re
             continue
         err = np.abs(g[ok] - r[ok])
         assert err.max() / mx <= plane_tol, f"{name}[..., {s}]: max|d|/max|ref| = {err.max() / mx:.3e}"
-        assert np.all(err <= rtol * np.abs(r[ok]) + atol_rel * mx), \
+        extra = floor[..., s][ok] if floor is not None else 0.0
+        assert not elementwise or np.all(err <= rtol * np.abs(r[ok]) + atol_rel * mx + extra), \
             f"{name}[..., {s}]: element-wise tolerance exceeded ({(err / (np.abs(r[ok]) + 1e-300)).max():.3e})"
 
 

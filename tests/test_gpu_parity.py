@@ -548,29 +548,23 @@ def _bench_pair(cfgname):
 def test_pruned_engine_matches_oracle_at_baseline_sizes(pf, ora, cfgname, scales):
     """BASELINE configs[1] (1024^2 land Bouguer) on scales {0, 10, 19} and configs[3] (2048^2 ocean free-air,
     wd > 0) on two scales: the default engine through the C ABI against ora64 on the very grids bench.py times.
-    Tolerance (tests/helpers.py): per scale plane max|d|/max|ref| <= 1e-9 over ALL cells, and element-wise rtol
-    1e-9 over the cells whose local wavelet power is above 1e-8 of the plane's maximum for both grids.  The
-    round-off of an FFT is relative to the plane, not to the cell: two correct transforms differ by ~1e-15 of the
-    plane's amplitude, so ratios formed in cells 1e-4 times weaker than the strongest one cannot agree to 1e-9 --
-    those cells (well under 1 % here, asserted) are held to the plane criterion only."""
+    Tolerance (tests/helpers.py): per scale plane max|d|/max|ref| <= 1e-9 and element-wise rtol 1e-9 for all four
+    maps.  For the two jackknife ERROR maps the element-wise bound carries one more term, 5e-11 * |value| (value =
+    the admittance / coherence of the cell): the error is the spread of eleven nearly equal means of ratios, so it
+    inherits the attainable accuracy of those ratios times |value| / spread (up to 30 at the smallest scale, 5e4
+    at the largest).  Two independent float64 CPU transforms of this very grid (ora64's Numerical-Recipes fourn
+    and numpy.fft) agree per coefficient only to 3e-14 of the plane maximum, i.e. to 2e-11 relative at the weakest
+    cells -- measured; that is the floor used here, not a property of the GPU path."""
     from plateflex_b200 import _lib
     from plateflex_b200.cpwt import fused
     cfg, topo, grav, k, k0 = _bench_pair(cfgname)
     _lib.clear_plans()
     ks = k[scales]
     got = fused.wlet_admit_coh(topo, grav, cfg["dx"], cfg["dy"], ks)
-    nt = os.cpu_count() or 1
-    w1 = ora.wlet_transform(topo, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=nt)
-    w2 = ora.wlet_transform(grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=nt)
-    ref = ora.wlet_admit_coh(w1, w2, prec=64)
-    p1, p2 = (np.abs(w1) ** 2).mean(axis=2), (np.abs(w2) ** 2).mean(axis=2)
-    del w1, w2
-    strong = (p1 >= 1e-8 * p1.max(axis=(0, 1))) & (p2 >= 1e-8 * p2.max(axis=(0, 1)))
-    assert strong.mean() > 0.99
+    ref = ora.admit_coh_from_grids(topo, grav, cfg["dx"], cfg["dy"], ks, k0=k0, prec=64, nthreads=os.cpu_count() or 1)
+    floors = {"ewl_admit": 5e-11 * np.abs(ref[0]), "ewl_coh": 5e-11 * np.abs(ref[2])}
     for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), got, ref):
-        assert_maps_close(a, b, f"{cfgname} {name}", rtol=np.inf)  # plane criterion, every cell
-        assert_maps_close(np.where(strong, a, 0.0), np.where(strong, b, 0.0), f"{cfgname} {name} (cells above 1e-4 of the "
-                          "plane amplitude)")
+        assert_maps_close(a, b, f"{cfgname} {name}", floor=floors.get(name))
     _lib.clear_plans()
 
 
@@ -759,11 +753,12 @@ def test_two_gpu_pipeline_equals_single_gpu_bit_for_bit(pf):
 
 
 @pytest.mark.parametrize("knobs", [{"PLATEFLEX_B200_V3": "on"}, {"PLATEFLEX_B200_V3": "1", "PLATEFLEX_B200_V3_OCC": "2"},
-                                   {"PLATEFLEX_B200_V3": "2", "PLATEFLEX_B200_V3_P1": "off"}])
+                                   {"PLATEFLEX_B200_V3": "2", "PLATEFLEX_B200_V3_P1": "off"}, {"PLATEFLEX_B200_V2H": "on"}])
 @pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[5:])
 def test_third_generation_pass_kernels_match_oracle(pf, ora, monkeypatch, knobs, nx, ny, dx, dy, kf):
     """The opt-in bulk-copy (cp.async.bulk + mbarrier) pass kernels of pfx_pruned_v3.cuh: transposed intermediate,
-    one / two line buffers, 2 or 3 CTAs per SM, with and without the third-generation pass 1."""
+    one / two line buffers, 2 or 3 CTAs per SM, with and without the third-generation pass 1; and the 128-thread
+    form of the second-generation pass 2 (v2h)."""
     from plateflex_b200 import _lib
     from plateflex_b200.cpwt import fused
     for name, value in knobs.items():
@@ -820,3 +815,42 @@ def test_nan_fill_and_gaussian_match_scipy(pf):
     want = ndimage.gaussian_filter(topo.data, 3, mode='nearest', truncate=4.0)
     want[topo.data > 0.] = 0.
     assert np.allclose(wd, want, rtol=1e-12, atol=1e-9) and np.array_equal(topo.water_depth, -1. * wd)
+
+
+def test_f2py_helper_exports_match_oracle(pf, ora):
+    """The subroutines numpy.f2py exports besides the drivers: flex.flexfilter_top/bot, decon,
+    tr_func (flex.f90:74-169) and cpwt_sub's npow2, defk, wave_function, against the oracle at 1e-12."""
+    import ctypes as C
+    from plateflex_b200.cpwt import cpwt
+    from plateflex_b200.flex import conf_flex, flex
+    pf.set_conf_flex()
+    conf_flex.wd, conf_flex.rhof, conf_flex.boug = 2500.0, conf_flex.rhow, 0
+    oc = ora.FlexConf(wd=2500.0, rhof=conf_flex.rhow, boug=0)
+    k = np.geomspace(3e-6, 4e-4, 17)
+    psi = 1e11 * (25e3) ** 3 / 12 / (1 - 0.25 ** 2) * k ** 4
+    lib = ora.lib()
+
+    def call(name, *arrays_and_scalars):
+        return getattr(lib, name)(C.byref(oc), C.c_int(len(k)), *arrays_and_scalars)
+
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    th_ref, ph_ref = np.empty_like(k), np.empty_like(k)
+    call("ora_flex_flexfilter_top", p(psi), p(th_ref))
+    call("ora_flex_flexfilter_bot", p(psi), p(ph_ref))
+    th, ph = flex.flexfilter_top(psi), flex.flexfilter_bot(psi)
+    assert np.allclose(th, th_ref, rtol=1e-13) and np.allclose(ph, ph_ref, rtol=1e-13)
+    refs = [np.empty_like(k) for _ in range(4)]
+    call("ora_flex_decon", p(th_ref), p(ph_ref), p(k), C.c_double(1.0), *[p(r) for r in refs])
+    for a, b in zip(flex.decon(th, ph, k, 1.0), refs):
+        assert np.allclose(a, b, rtol=1e-12)
+    adm, coh = flex.tr_func(*refs, 0.3, 1.1)
+    a_ref, c_ref = ora.real_xspec_functions(k, 25.0, 0.3, 1.1, oc)
+    assert np.allclose(adm.real, a_ref, rtol=1e-12) and np.allclose(coh, c_ref, rtol=1e-12) and np.abs(adm.imag).max() > 0
+    assert [cpwt.npow2(n) for n in (1, 3, 684)] == [2, 4, 1024]
+    kx, ky = cpwt.defk(16, 10, 5.0, 7.0)
+    rkx, rky = ora.defk(16, 10, 5.0, 7.0)
+    assert np.allclose(kx, rkx, rtol=1e-15) and np.allclose(ky, rky, rtol=1e-15) and kx[8] > 0
+    w = cpwt.wave_function(kx, ky, pf.cf_wt.k0, 30.0, 0.4)
+    rw = ora.wave_function(kx, ky, pf.cf_wt.k0, 30.0, 0.4)
+    assert w.shape == (16, 10) and np.allclose(w, rw, rtol=1e-12, atol=1e-300)
+    pf.set_conf_flex()
