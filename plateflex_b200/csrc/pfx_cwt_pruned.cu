@@ -30,6 +30,7 @@
 #include "pfx_pruned.hpp"
 #include "pfx_pruned_v2.cuh"
 #include "pfx_pruned_v3.cuh"
+#include "pfx_pruned_v4.cuh"
 
 namespace pfx {
 
@@ -164,6 +165,9 @@ struct PrunedState {
     std::vector<int> v3x_nbuf, v3x_ctas, v3y_nbuf, v3y_ctas;
     // 128-thread form of the second-generation pass 2 (namespace v2h): CTAs resident per SM, 0 = not used
     std::vector<int> v2hx_ctas;
+    // fourth-generation (radix-16, 128-thread) kernels of pfx_pruned_v4.cuh: CTAs resident on the device, 0 = not used
+    std::vector<int> v4x_ctas, v4y_ctas;
+    int v4_waves_p2 = 1;  // pass-2 grid as a multiple of the resident CTAs (PLATEFLEX_B200_V4_WAVES)
     int v3_occ = 3;  // CTAs per SM the v3 kernels are compiled for (PLATEFLEX_B200_V3_OCC = 2 | 3)
     int nsm = 148;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
@@ -221,6 +225,16 @@ int plan_init_pruned(pfx_plan *pl)
     st->v3y_nbuf.assign(ns, 0);
     st->v3y_ctas.assign(ns, 0);
     st->v2hx_ctas.assign(ns, 0);
+    st->v4x_ctas.assign(ns, 0);
+    st->v4y_ctas.assign(ns, 0);
+    // PLATEFLEX_B200_V4 = "on" | "p1" | "p2" | "off": radix-16 pass kernels for both passes, one of them, or none
+    const char *v4_env = getenv("PLATEFLEX_B200_V4");
+    const bool v4_p1 = v4_env && (!strcmp(v4_env, "on") || !strcmp(v4_env, "p1"));
+    const bool v4_p2 = v4_env && (!strcmp(v4_env, "on") || !strcmp(v4_env, "p2"));
+    {
+        const char *w = getenv("PLATEFLEX_B200_V4_WAVES");
+        if (w && atoi(w) > 0) st->v4_waves_p2 = atoi(w);
+    }
     // PLATEFLEX_B200_V2H = "on": pass 2 with 128-thread CTAs (parts of 1024 elements) where the FFT length allows
     const char *v2h_env = getenv("PLATEFLEX_B200_V2H");
     const bool v2h_on = v2h_env && !strcmp(v2h_env, "on");
@@ -408,7 +422,14 @@ int plan_init_pruned(pfx_plan *pl)
         } else {
             PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
         }
-        if (v2h_on && !st->v3x_nbuf[is] && st->v2x[is] >= 0 && sd.ax.logL <= 10) {
+        if (v4_p1 && !st->v3y_nbuf[is] && st->v2y[is] >= 0) {
+            PFX_CHECK(v4_configure_p1(sd.ay.logL, sd.ay.N > 2048, &res));
+            st->v4y_ctas[is] = std::max(res, 1) * st->nsm;
+        }
+        if (v4_p2 && !st->v3x_nbuf[is] && st->v2x[is] >= 0) {
+            PFX_CHECK(v4_configure_p2(sd.ax.logL, sd.ax.N > 2048, &res));
+            st->v4x_ctas[is] = std::max(res, 1) * st->nsm;
+        } else if (v2h_on && !st->v3x_nbuf[is] && st->v2x[is] >= 0 && sd.ax.logL <= 10) {
             PFX_CHECK(v2h_configure_p2(sd.ax.logL, sd.ax.N > 1024, &res));
             st->v2hx_ctas[is] = std::max(res, 1) * st->nsm;
         } else if (st->v3x_nbuf[is]) {
@@ -510,7 +531,11 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     {
         NvtxRange r("pfx:pass1");
         ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
-        if (st->v3y_nbuf[is]) {
+        if (st->v4y_ctas[is]) {
+            v4::V4Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v4y_ctas[is] / ntr);
+            PFX_CHECK(v4_launch_p1(va, sd.ay.logL, sd.ay.N > 2048, dim3(std::min(sd.kamax, ctas), ntr), pl->stream));
+        } else if (st->v3y_nbuf[is]) {
             const int multi = (st->v2y[is] >> 5) & 1;
             v3::V3Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1), st->v3y_nbuf[is]};
             // a few waves: the number of columns differs between azimuths
@@ -530,7 +555,11 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     {
         NvtxRange r("pfx:pass2");
         ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
-        if (st->v3x_nbuf[is]) {
+        if (st->v4x_ctas[is]) {
+            v4::V4Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
+            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v4_waves_p2 * st->v4x_ctas[is] / ntr);
+            PFX_CHECK(v4_launch_p2(va, sd.ax.logL, sd.ax.N > 2048, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+        } else if (st->v3x_nbuf[is]) {
             const int multi = (st->v2x[is] >> 5) & 1;
             v3::V3Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1), st->v3x_nbuf[is]};
             // every transform has the same number of rows: one wave of persistent CTAs

@@ -10,16 +10,16 @@ namespace prn {
 
 constexpr int NT = PRN_NT;
 
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+__host__ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
 // In-register inverse DFT (exp(+i...)) of R = 2, 4, 8 points, natural order in and out.
 template <int R>
-__device__ __forceinline__ void dft(double2 (&v)[R])
+__host__ __device__ __forceinline__ void dft(double2 (&v)[R])
 {
     if constexpr (R == 2) {
         const double2 a = v[0], b = v[1];
