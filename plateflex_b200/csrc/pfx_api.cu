@@ -281,8 +281,10 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
     if ((rc = pl->alloc((void **)&pl->d_u2, pl->NX * sizeof(double)))) return fail(rc);
     if ((rc = pl->alloc((void **)&pl->d_v2, pl->NY * sizeof(double)))) return fail(rc);
     if ((rc = pl->alloc((void **)&pl->d_partial, 512 * sizeof(double)))) return fail(rc);
-    for (int g = 0; g < 2; g++)
-        if ((rc = pl->alloc((void **)&pl->d_spec[g], P * sizeof(double2)))) return fail(rc);
+    // the pruned engine allocates the padded spectra itself unless it can use the cosine-transform form (pfx_dct.cu)
+    if (engine != PFX_ENGINE_PRUNED)
+        for (int g = 0; g < 2; g++)
+            if ((rc = pl->alloc((void **)&pl->d_spec[g], P * sizeof(double2)))) return fail(rc);
     if ((rc = plan_init_axes(pl))) return fail(rc);
     {
         cudaError_t e = cudaStreamCreateWithFlags(&pl->s_aux, cudaStreamNonBlocking);
@@ -462,8 +464,9 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     const size_t nxy = (size_t)pl->nx * pl->ny;
     {
         NvtxRange r("pfx:forward");
-        PFX_CHECK(forward_spectrum(pl, g1, 0));
-        if (g2) PFX_CHECK(forward_spectrum(pl, g2, 1));
+        const bool pr = pl->engine == PFX_ENGINE_PRUNED;
+        PFX_CHECK(pr ? pruned_forward(pl, g1, 0) : forward_spectrum(pl, g1, 0));
+        if (g2) PFX_CHECK(pr ? pruned_forward(pl, g2, 1) : forward_spectrum(pl, g2, 1));
     }
     const bool pruned = pl->engine == PFX_ENGINE_PRUNED;
     if (pruned) {
@@ -628,7 +631,7 @@ static int transform_to_host(pfx_plan *pl, const double *grid, int is0, int is1,
     PFX_CHECK(pl->scratch(2, slab_bytes, &d_slab[0]));
     PFX_CHECK(pl->scratch(3, slab_bytes, &d_slab[1]));
     PFX_CUDA(cudaMemcpyAsync(d_g, grid, nxy * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
-    PFX_CHECK(forward_spectrum(pl, d_g, 0));
+    PFX_CHECK(pl->engine == PFX_ENGINE_PRUNED ? pruned_forward(pl, d_g, 0) : forward_spectrum(pl, d_g, 0));
     if (pl->engine == PFX_ENGINE_PRUNED) PFX_CHECK(pruned_prepare(pl, 1));
     auto enqueue = [&](int is, int b) -> int {  // planes of scale `is`, cropped into slab b
         PlaneView v;

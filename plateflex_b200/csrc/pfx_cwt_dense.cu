@@ -149,6 +149,17 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
+// mean of the nx*ny grid (deterministic two-stage sum), left on the device
+int grid_mean(pfx_plan *pl, const double *grid_dev, const double **mean_dev)
+{
+    const size_t n = (size_t)pl->nx * pl->ny;
+    sum_partial_kernel<<<SUM_BLOCKS, SUM_THREADS, 0, pl->stream>>>(grid_dev, n, pl->d_partial);
+    sum_final_kernel<<<1, SUM_THREADS, 0, pl->stream>>>(pl->d_partial, SUM_BLOCKS, 1.0 / (double)n);
+    PFX_CUDA(cudaGetLastError());
+    *mean_dev = pl->d_partial + SUM_BLOCKS;
+    return PFX_OK;
+}
+
 int forward_spectrum(pfx_plan *pl, const double *grid_dev, int slot)
 {
     const size_t n = (size_t)pl->nx * pl->ny, P = (size_t)pl->NX * pl->NY;

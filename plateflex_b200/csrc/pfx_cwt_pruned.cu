@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "pfx_dct.hpp"
 #include "pfx_plan.hpp"
 #include "pfx_pruned.hpp"
 #include "pfx_pruned_v2.cuh"
@@ -167,7 +168,8 @@ struct PrunedState {
     std::vector<int> v2hx_ctas;
     // fourth-generation (radix-16, 128-thread) kernels of pfx_pruned_v4.cuh: CTAs resident on the device, 0 = not used
     std::vector<int> v4x_ctas, v4y_ctas;
-    int v4_waves_p2 = 1;  // pass-2 grid as a multiple of the resident CTAs (PLATEFLEX_B200_V4_WAVES)
+    DctState *dct = nullptr;  // cosine-transform form of the forward spectra and of Z (pfx_dct.cu), or null
+    int v4_waves_p2 = 2;  // pass-2 grid as a multiple of the resident CTAs (PLATEFLEX_B200_V4_WAVES; 2 measured best)
     int v3_occ = 3;  // CTAs per SM the v3 kernels are compiled for (PLATEFLEX_B200_V3_OCC = 2 | 3)
     int nsm = 148;
     double cur_ce[PFX_NA] = {};  // c*E of the scale whose planes currently sit in W
@@ -227,10 +229,12 @@ int plan_init_pruned(pfx_plan *pl)
     st->v2hx_ctas.assign(ns, 0);
     st->v4x_ctas.assign(ns, 0);
     st->v4y_ctas.assign(ns, 0);
-    // PLATEFLEX_B200_V4 = "on" | "p1" | "p2" | "off": radix-16 pass kernels for both passes, one of them, or none
+    // PLATEFLEX_B200_V4 = "on" | "p1" | "p2" | "off": radix-16 pass kernels for both passes, one of them, or none.
+    // Default "p2": measured on B200 (profiles/README.md) pass 2 gains 7-8 % (L = 128 and 1024: 16-18 %), pass 1
+    // does not (its lines are short and few; the second generation keeps three CTAs of 256 threads per SM there).
     const char *v4_env = getenv("PLATEFLEX_B200_V4");
     const bool v4_p1 = v4_env && (!strcmp(v4_env, "on") || !strcmp(v4_env, "p1"));
-    const bool v4_p2 = v4_env && (!strcmp(v4_env, "on") || !strcmp(v4_env, "p2"));
+    const bool v4_p2 = !v4_env || !strcmp(v4_env, "on") || !strcmp(v4_env, "p2");
     {
         const char *w = getenv("PLATEFLEX_B200_V4_WAVES");
         if (w && atoi(w) > 0) st->v4_waves_p2 = atoi(w);
@@ -334,7 +338,17 @@ int plan_init_pruned(pfx_plan *pl)
     for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Wbuf[b], 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
     st->W = st->Wbuf[0];
     PFX_CHECK(dalloc((void **)&st->zc, (size_t)nx * ny * sizeof(double2)));
-    PFX_CHECK(dalloc((void **)&st->zplanes, P * sizeof(double2)));
+    // Power-of-two grids: spectra and Z through cosine transforms of the unmirrored grid, provided every scale's
+    // pass 1 is a kernel that can read that form (second / fourth generation)
+    bool use_dct = dct_applicable(pl);
+    for (int is = 0; is < ns; is++) use_dct = use_dct && st->v2y[is] >= 0 && !st->v3y_nbuf[is];
+    if (use_dct) {
+        PFX_CHECK(dct_init(pl, &st->dct, st->owned));
+    } else {
+        PFX_CHECK(dalloc((void **)&st->zplanes, P * sizeof(double2)));
+        for (int g = 0; g < 2; g++)
+            if (!pl->d_spec[g]) PFX_CHECK(pl->alloc((void **)&pl->d_spec[g], P * sizeof(double2)));
+    }
 
     root_kernel<<<(NX + 255) / 256, 256, 0, pl->stream>>>(NX, st->rootx);
     root_kernel<<<(NY + 255) / 256, 256, 0, pl->stream>>>(NY, st->rooty);
@@ -380,7 +394,7 @@ int plan_init_pruned(pfx_plan *pl)
     // dense inverse plan for the admissibility term (one plane serves both grids), y-fastest layout
     int n[2] = {NX, NY};
     size_t need = pl->fft_work_bytes;
-    {
+    if (!st->dct) {
         size_t ws = 0;
         PFX_CUFFT(cufftCreate(&st->fft_z));
         st->fft_z_ok = true;
@@ -395,7 +409,7 @@ int plan_init_pruned(pfx_plan *pl)
         pl->fft_work_bytes = need;
         PFX_CUFFT(cufftSetWorkArea(pl->fft_fwd, pl->d_fft_work));
     }
-    PFX_CUFFT(cufftSetWorkArea(st->fft_z, pl->d_fft_work));
+    if (st->fft_z_ok) PFX_CUFFT(cufftSetWorkArea(st->fft_z, pl->d_fft_work));
 
     for (int is = 0; is < ns; is++) {
         const ScaleDesc &sd = st->sd[is];
@@ -422,8 +436,9 @@ int plan_init_pruned(pfx_plan *pl)
         } else {
             PFX_CHECK(prn_configure_pass1(sd.ay.logL, sd.ay.pad, st->smem1));
         }
+        if (st->dct && st->v2y[is] >= 0) st->v2y[is] = (st->v2y[is] & ~0x1f) | 1 | (1 << 6);  // single line, no prefetch
         if (v4_p1 && !st->v3y_nbuf[is] && st->v2y[is] >= 0) {
-            PFX_CHECK(v4_configure_p1(sd.ay.logL, sd.ay.N > 2048, &res));
+            PFX_CHECK(v4_configure_p1(sd.ay.logL, sd.ay.N > 2048, st->dct != nullptr, &res));
             st->v4y_ctas[is] = std::max(res, 1) * st->nsm;
         }
         if (v4_p2 && !st->v3x_nbuf[is] && st->v2x[is] >= 0) {
@@ -465,6 +480,7 @@ void plan_free_pruned(pfx_plan *pl)
     if (!st) return;
     if (st->fft_z_ok) cufftDestroy(st->fft_z);
     cudaStreamSynchronize(pl->stream);
+    dct_free(st->dct);
     for (auto &pb : st->owned) {
         cudaFree(pb.first);
         pl->device_bytes -= pb.second;
@@ -474,9 +490,17 @@ void plan_free_pruned(pfx_plan *pl)
 }
 
 // Once per set of forward spectra: (Z_0, Z_1) = crop(IFFT2(u2*v2*(X_0 + i X_1)))/P.
+int pruned_forward(pfx_plan *pl, const double *grid_dev, int slot)
+{
+    PrunedState *st = state_of(pl);
+    if (st && st->dct) return dct_forward(pl, st->dct, grid_dev, slot);
+    return forward_spectrum(pl, grid_dev, slot);
+}
+
 int pruned_prepare(pfx_plan *pl, int ngrids)
 {
     PrunedState *st = state_of(pl);
+    if (st->dct) return dct_prepare(pl, st->dct, ngrids, st->zc);
     const size_t P = (size_t)pl->NX * pl->NY;
     ProfScope prof(pl, PFX_KC_PREPARE, pl->stream);
     zmul_kernel<<<dim3((pl->NY + 255) / 256, pl->NX), 256, 0, pl->stream>>>(
@@ -508,6 +532,12 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     a.ngrids = ngrids;
     a.spec0 = pl->d_spec[0];
     a.spec1 = pl->d_spec[1];
+    if (st->dct) {
+        a.dct0 = st->dct->D;
+        a.dct1 = st->dct->D + (size_t)pl->nx * pl->ny;
+        a.phx = st->dct->phx;
+        a.phy = st->dct->phy;
+    }
     a.tabu = st->tabu;
     a.tabv = st->tabv;
     a.twa = st->twa;
@@ -534,7 +564,7 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
         if (st->v4y_ctas[is]) {
             v4::V4Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
             const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v4y_ctas[is] / ntr);
-            PFX_CHECK(v4_launch_p1(va, sd.ay.logL, sd.ay.N > 2048, dim3(std::min(sd.kamax, ctas), ntr), pl->stream));
+            PFX_CHECK(v4_launch_p1(va, sd.ay.logL, sd.ay.N > 2048, st->dct != nullptr, dim3(std::min(sd.kamax, ctas), ntr), pl->stream));
         } else if (st->v3y_nbuf[is]) {
             const int multi = (st->v2y[is] >> 5) & 1;
             v3::V3Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1), st->v3y_nbuf[is]};

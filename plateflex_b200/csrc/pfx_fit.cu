@@ -618,6 +618,10 @@ __device__ __forceinline__ double rcp_nr(double x)
 // exp(-k*(zc+wd)), exp(-k*wd) are kept per thread in shared memory.  No lane ever idles on the
 // small dense algebra of the optimiser, which made this 3x cheaper than one warp per cell.
 constexpr int FIT_NT = 128;
+#ifndef FIT_UNROLL
+#define FIT_UNROLL 2  // scales evaluated side by side in the model loop (independent dependency chains)
+#endif
+constexpr int FIT_UNROLL_N = FIT_UNROLL;
 #ifndef FIT_MIN_BLOCKS
 #define FIT_MIN_BLOCKS 3
 #endif
@@ -699,7 +703,7 @@ __global__ void __launch_bounds__(FIT_NT, CACHE ? 2 : FIT_MIN_BLOCKS) fit_cell_k
             double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
             for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
-#pragma unroll 2
+#pragma unroll FIT_UNROLL_N
             for (int s = 0; s < a.ns; s++) {
                 FlexK fk;
                 fk.k4d = k4[s];
@@ -809,7 +813,7 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
         double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
         for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
-#pragma unroll 2
+#pragma unroll FIT_UNROLL_N
         for (int s = 0; s < a.ns; s++) {
             FlexK fk;
             fk.k4d = k4[s];

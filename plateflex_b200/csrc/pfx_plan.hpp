@@ -116,6 +116,7 @@ struct ProfScope {
 // K1: mirror + de-mean + zero-pad (cpwt.f90:100-116, cpwt_sub.f90:435-449) then one forward FFT
 // (cpwt.f90:122) of grid g (device pointer, C order) into plan->d_spec[slot].
 int forward_spectrum(pfx_plan *pl, const double *grid_dev, int slot);
+int grid_mean(pfx_plan *pl, const double *grid_dev, const double **mean_dev);
 
 // Dense engine: all 11 azimuth planes of scale `is` for ngrids spectra -> plan->d_planes
 // (plane p = ia + 11*g), as un-normalised, un-shifted inverse FFTs.
@@ -129,6 +130,9 @@ int plan_init_axes(pfx_plan *pl);
 int plan_init_pruned(pfx_plan *pl);
 void plan_free_pruned(pfx_plan *pl);
 int pruned_prepare(pfx_plan *pl, int ngrids);          // admissibility transform Z, once per set of spectra
+// forward spectrum of grid `slot` for the pruned engine: the cosine-transform form (pfx_dct.cu) on power-of-two
+// grids, else forward_spectrum
+int pruned_forward(pfx_plan *pl, const double *grid_dev, int slot);
 int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);  // -> compact W planes of scale `is`
 PlaneView pruned_view(const pfx_plan *pl, int g);
 int pruned_num_buffers(const pfx_plan *pl);

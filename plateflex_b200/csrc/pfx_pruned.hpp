@@ -71,6 +71,11 @@ struct PrunedArgs {
     // of the third-generation pass 2 (pfx_pruned_v3.cuh) reads it after one bulk copy of the line
     int t_tr = 0, t_lp = 0, t_pad = 0;
     double2 *W;                    // [t][j][i] output planes (main Gaussian term only)
+    // Cosine-transform form of the spectra (pfx_dct.cu; power-of-two grids, NX = 2 nx, NY = 2 ny): when dct0 is set
+    // pass 1 reads  X_g[a][b] = phx[a] phy[b] D_g[|a|][|b|]  (D real, [nx][ny], zero at |a| = nx or |b| = ny)
+    // instead of spec0 / spec1; the x phase is applied with the u1 weight when the column is stored.
+    const double *dct0 = nullptr, *dct1 = nullptr;
+    const double2 *phx = nullptr, *phy = nullptr;
 };
 
 inline size_t prn_plane_elems(const AxisDesc &A) { return (size_t)((A.L - 1) + (A.pad ? (A.L - 1) >> 3 : 0) + 1) * A.rc; }

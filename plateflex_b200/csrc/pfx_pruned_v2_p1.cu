@@ -6,11 +6,16 @@ namespace pfx {
 namespace {
 using KernelFn = void (*)(v2::V2Args);
 
-// variant = cpc | (prefetch << 4) | (multi << 5); two lines per CTA only without MULTI / PREFETCH (registers)
+// variant = cpc | (prefetch << 4) | (multi << 5) | (dct << 6); two lines per CTA only without MULTI / PREFETCH
+// (registers); dct: the spectrum is read in its cosine-transform form (pfx_dct.cu), single line, no prefetch
 template <int LOGL>
 KernelFn pick(int variant)
 {
-    const int cpc = variant & 15, pre = (variant >> 4) & 1, multi = (variant >> 5) & 1;
+    const int cpc = variant & 15, pre = (variant >> 4) & 1, multi = (variant >> 5) & 1, dct = (variant >> 6) & 1;
+    if (dct) {
+        if (cpc != 1 || pre) return nullptr;
+        return multi ? v2::pass1_kernel<LOGL, 1, true, false, true> : v2::pass1_kernel<LOGL, 1, false, false, true>;
+    }
     if (cpc == 2) return (pre || multi) ? nullptr : v2::pass1_kernel<LOGL, 2, false, false>;
     if (multi) return pre ? v2::pass1_kernel<LOGL, 1, true, true> : v2::pass1_kernel<LOGL, 1, true, false>;
     return pre ? v2::pass1_kernel<LOGL, 1, false, true> : v2::pass1_kernel<LOGL, 1, false, false>;

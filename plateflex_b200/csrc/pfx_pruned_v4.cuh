@@ -377,12 +377,15 @@ __global__ void __launch_bounds__(NT, MULTI ? 3 : 4) pass2_kernel(V4Args a)
 }
 
 // ---- pass 1: y-direction transforms, one spectrum column per group -------------------------------------------
+template <bool DCT>
 struct Pass1Group {
     const double2 *spec;  // padded spectrum [a][b] (y-wavenumber fastest)
     const double *tv;     // v1 weights of this azimuth [L]
     const double *tu;     // (c/P) u1 weights of this azimuth [Lx]
     double2 *T;           // intermediate (layout: prn_t_column)
     const PrunedArgs *pa;
+    const double *dct;         // cosine-transform spectrum D[|a|][|b|] of this grid, or null (pfx_dct.cu)
+    const double2 *phx, *phy;  // ... and its phases e^{i pi a/NX}, e^{i pi b/NY}
     int t;
     int NX, NYm, ny, alo, ka, blo, logr;
     __device__ __forceinline__ int first() const { return blockIdx.x; }
@@ -390,8 +393,15 @@ struct Pass1Group {
     __device__ __forceinline__ int next(int g) const { return g + gridDim.x; }
     __device__ __forceinline__ double2 load(int m, int mb) const
     {
-        const double2 x = __ldg(spec + (size_t)((alo + m) & (NX - 1)) * (NYm + 1) + ((blo + mb) & NYm));
         const double wv = tv[mb];
+        if (DCT) {
+            const int a = alo + m, b = blo + mb, aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
+            if (2 * aa >= NX || bb >= ny) return make_double2(0., 0.);  // D[nx][.] = D[.][ny] = 0
+            const double d = __ldg(dct + (size_t)aa * ny + bb) * wv;
+            const double2 ph = __ldg(phy + (b & NYm));
+            return make_double2(d * ph.x, d * ph.y);
+        }
+        const double2 x = __ldg(spec + (size_t)((alo + m) & (NX - 1)) * (NYm + 1) + ((blo + mb) & NYm));
         return make_double2(x.x * wv, x.y * wv);
     }
     __device__ __forceinline__ void store(int m, int q, int rho, double2 v) const
@@ -401,12 +411,18 @@ struct Pass1Group {
             const double wu = tu[m];
             size_t js;
             const size_t o = prn_t_column(*pa, t, m, alo, js);
-            T[o + (size_t)j * js] = make_double2(v.x * wu, v.y * wu);
+            if (DCT) {
+                const double2 ph = __ldg(phx + ((alo + m) & (NX - 1)));
+                const double2 w = make_double2(ph.x * wu, ph.y * wu);
+                T[o + (size_t)j * js] = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+            } else {
+                T[o + (size_t)j * js] = make_double2(v.x * wu, v.y * wu);
+            }
         }
     }
 };
 
-template <int LOGL, bool MULTI>
+template <int LOGL, bool MULTI, bool DCT>
 __global__ void __launch_bounds__(NT, MULTI ? 3 : 4) pass1_kernel(V4Args a)
 {
     using G = Geo<LOGL>;
@@ -417,8 +433,11 @@ __global__ void __launch_bounds__(NT, MULTI ? 3 : 4) pass1_kernel(V4Args a)
     if ((int)blockIdx.x >= sd.ka[ia]) return;
     double2 *stw = smem + G::PLANE;
     load_stage_twiddles<LOGL>(stw, A.logN, a.p.rooty);
-    Pass1Group grp;
+    Pass1Group<DCT> grp;
     grp.spec = g ? a.p.spec1 : a.p.spec0;
+    grp.dct = g ? a.p.dct1 : a.p.dct0;
+    grp.phx = a.p.phx;
+    grp.phy = a.p.phy;
     grp.tv = a.p.tabv + sd.tabv + ((size_t)ia << LOGL);
     grp.tu = a.p.tabu + sd.tabu + (size_t)ia * sd.ax.L;
     grp.T = a.p.T;
@@ -444,9 +463,9 @@ inline size_t smem_bytes()
 }  // namespace v4
 
 // launchers (pfx_pruned_v4_p1.cu, pfx_pruned_v4_p2.cu); resident receives the CTAs of this kernel per SM
-int v4_configure_p1(int logL, int multi, int *resident);
+int v4_configure_p1(int logL, int multi, int dct, int *resident);
 int v4_configure_p2(int logL, int multi, int *resident);
-int v4_launch_p1(const v4::V4Args &a, int logL, int multi, dim3 grid, cudaStream_t st);
+int v4_launch_p1(const v4::V4Args &a, int logL, int multi, int dct, dim3 grid, cudaStream_t st);
 int v4_launch_p2(const v4::V4Args &a, int logL, int multi, dim3 grid, cudaStream_t st);
 
 }  // namespace pfx

@@ -9,10 +9,11 @@ using KernelFn = void (*)(v4::V4Args);
 template <int LOGL>
 KernelFn pick(int multi)
 {
-    return multi ? v4::pass1_kernel<LOGL, true> : v4::pass1_kernel<LOGL, false>;
+    if (multi & 2) return (multi & 1) ? v4::pass1_kernel<LOGL, true, true> : v4::pass1_kernel<LOGL, false, true>;
+    return (multi & 1) ? v4::pass1_kernel<LOGL, true, false> : v4::pass1_kernel<LOGL, false, false>;
 }
 
-KernelFn kernel_for(int logL, int multi)
+KernelFn kernel_for(int logL, int multi)  // multi | (dct << 1)
 {
     switch (logL) {
         case 5: return pick<5>(multi);
@@ -41,9 +42,9 @@ size_t smem_for(int logL)
 }
 }  // namespace
 
-int v4_configure_p1(int logL, int multi, int *resident)
+int v4_configure_p1(int logL, int multi, int dct, int *resident)
 {
-    KernelFn f = kernel_for(logL, multi);
+    KernelFn f = kernel_for(logL, (multi ? 1 : 0) | (dct ? 2 : 0));
     PFX_ARG(f != nullptr, "pruned v4 pass 1: unsupported FFT length");
     const size_t smem = smem_for(logL);
     PFX_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -51,9 +52,9 @@ int v4_configure_p1(int logL, int multi, int *resident)
     return PFX_OK;
 }
 
-int v4_launch_p1(const v4::V4Args &a, int logL, int multi, dim3 grid, cudaStream_t st)
+int v4_launch_p1(const v4::V4Args &a, int logL, int multi, int dct, dim3 grid, cudaStream_t st)
 {
-    KernelFn f = kernel_for(logL, multi);
+    KernelFn f = kernel_for(logL, (multi ? 1 : 0) | (dct ? 2 : 0));
     PFX_ARG(f != nullptr, "pruned v4 pass 1: unsupported FFT length");
     f<<<grid, v4::NT, smem_for(logL), st>>>(a);
     PFX_CUDA(cudaGetLastError());

@@ -70,35 +70,35 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
     return jk_spread(v2);
 }
 
-// The same two quotients added straight into the running sums of the walk (sa += ad, sc += co) with one fused
-// multiply-add each: when a sum is 0 the common factor is replaced by 0, so both sums stay as they are.
+// cpwt_sub.f90:329-335: co = Re(xp)^2/(p1*p2), ad = Re(xp)/p1, both 0 when a sum is 0 -- added straight into the
+// running sums of the walk (sa += ad, sc += co).
+// FAST (every non-zero per-azimuth power of the cell lies in [1e-150, 1e150], checked once per cell by the caller,
+// so no prefix product can underflow or overflow): one branch-free reciprocal serves both quotients
+// (ad = xp*p2/(p1*p2)) with one fused multiply-add each; the sums are non-negative, so "a sum is 0" is "the
+// product is 0", read from its exponent and mantissa bits with integer instructions; results differ from the
+// reference's IEEE divisions by a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
+// Otherwise (grids of extreme amplitude): the reference's own guard (p1 /= 0 .and. p2 /= 0) and IEEE divisions,
+// formed as (xp/p1)*(xp/p2) so that the product of the two sums is never taken.
+template <bool FAST>
 __device__ __forceinline__ void ratio_acc(double q1, double q2, double qx, double &sa, double &sc)
 {
-    const double prod = q1 * q2;
-    const double xr = qx * fast_rcp(prod);
-    const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
-    const double f = ok ? xr : 0.0;
-    sc = fma(qx, f, sc);
-    sa = fma(q2, f, sa);
-}
-
-__device__ __forceinline__ void ratio(double q1, double q2, double qx, double &ad, double &co)
-{
-    // cpwt_sub.f90:329-335: co = Re(xp)^2/(p1*p2), ad = Re(xp)/p1, both 0 when a sum is 0.
-    // One branch-free reciprocal serves both quotients (ad = xp*p2/(p1*p2)), and the divisions by the
-    // constants na, na-1 are multiplications: the results differ from the reference's IEEE divisions by
-    // a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
-    // The sums are non-negative, so "a sum is 0" is "the product is 0"; the test reads the exponent and
-    // mantissa bits with integer instructions and leaves the FP64 pipe to the arithmetic.
-    const double prod = q1 * q2;
-    const double xr = qx * fast_rcp(prod);
-    const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
-    co = ok ? qx * xr : 0.0;
-    ad = ok ? q2 * xr : 0.0;
+    if (FAST) {
+        const double prod = q1 * q2;
+        const double xr = qx * fast_rcp(prod);
+        const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
+        const double f = ok ? xr : 0.0;
+        sc = fma(qx, f, sc);
+        sa = fma(q2, f, sa);
+    } else if (q1 != 0.0 && q2 != 0.0) {
+        const double ad = qx / q1;
+        sa += ad;
+        sc += ad * (qx / q2);
+    }
 }
 
 // cpwt_sub.f90:298-366, same shared-prefix walk: 10 + 55 ratio evaluations
 // instead of the reference's 110.
+template <bool FAST>
 __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const double (&s2)[NA], const double (&xr)[NA],
                                              double &ead, double &eco)
 {
@@ -112,7 +112,7 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             q1 += s1[a2];
             q2 += s2[a2];
             qx += xr[a2];
-            ratio_acc(q1, q2, qx, sa, sc);
+            ratio_acc<FAST>(q1, q2, qx, sa, sc);
         }
         ad2[a] = sa * (1.0 / (double)(NA - 1));
         co2[a] = sc * (1.0 / (double)(NA - 1));
@@ -120,11 +120,28 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             p1 += s1[a];
             p2 += s2[a];
             px += xr[a];
-            ratio_acc(p1, p2, px, cad, cco);
+            ratio_acc<FAST>(p1, p2, px, cad, cco);
         }
     }
     ead = jk_spread(ad2);
     eco = jk_spread(co2);
+}
+
+// The rare path, out of line so that it costs the common one neither registers nor instruction cache.
+struct JkTriples {
+    double s1[NA], s2[NA], xr[NA];
+};
+__device__ __noinline__ void jk_admit_coh_exact(const JkTriples t, double *ead, double *eco)
+{
+    jk_admit_coh<false>(t.s1, t.s2, t.xr, *ead, *eco);
+}
+
+// non-zero and outside [1e-150, 1e150] (or not finite): high word of the double against the two exponents
+__device__ __forceinline__ bool extreme(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu;
+    const bool zero = (hi | (unsigned)__double2loint(v)) == 0u;
+    return !zero && (hi < 0x20ca2fe7u || hi > 0x5f138d35u);  // 1e-150 = 0x20ca2fe76a3f9475, 1e150 = 0x5f138d352e5096af
 }
 
 // the (real) admissibility terms of both grids at cell (i, j)
@@ -201,12 +218,14 @@ __global__ void __launch_bounds__(128, OCC)
     } else {
         double s1[NA], s2[NA], xr[NA];
         double t1 = 0.0, t2 = 0.0, tx = 0.0;
+        bool odd = false;
 #pragma unroll
         for (int a = 0; a < NA; a++) {
             const double2 u = load_w(w1, a, i, j, z1), v = load_w(w2, a, i, j, z2);
             s1[a] = fabs(u.x * u.x + u.y * u.y);  // cpwt.f90:333
             s2[a] = fabs(v.x * v.x + v.y * v.y);  // cpwt.f90:334
             xr[a] = u.x * v.x + u.y * v.y;        // Re(w1*CONJG(w2)), cpwt.f90:335
+            odd = odd || extreme(s1[a]) || extreme(s2[a]);
             t1 += s1[a];
             t2 += s2[a];
             tx += xr[a];
@@ -214,10 +233,21 @@ __global__ void __launch_bounds__(128, OCC)
         t1 = t1 * (1.0 / (double)NA);  // cpwt.f90:348-350
         t2 = t2 * (1.0 / (double)NA);
         tx = tx * (1.0 / (double)NA);
-        put<F32>(out0, o, tx / t1);                // cpwt.f90:354
-        put<F32>(out2, o, (tx * tx) / (t1 * t2));  // cpwt.f90:355
+        put<F32>(out0, o, tx / t1);                                            // cpwt.f90:354
+        put<F32>(out2, o, odd ? (tx / t1) * (tx / t2) : (tx * tx) / (t1 * t2));  // cpwt.f90:355
         double ead, eco;
-        jk_admit_coh(s1, s2, xr, ead, eco);
+        if (odd) {
+            JkTriples t;
+#pragma unroll
+            for (int a = 0; a < NA; a++) {
+                t.s1[a] = s1[a];
+                t.s2[a] = s2[a];
+                t.xr[a] = xr[a];
+            }
+            jk_admit_coh_exact(t, &ead, &eco);
+        } else {
+            jk_admit_coh<true>(s1, s2, xr, ead, eco);
+        }
         put<F32>(out1, o, ead);
         put<F32>(out3, o, eco);
     }

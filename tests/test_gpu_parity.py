@@ -34,6 +34,10 @@ CASES = [  # nx, ny, dx, dy, wavenumbers (rad/m)
     (24, 520, 5.0, 5.0, None),
     (1030, 20, 5.0, 5.0, ("ladder", 2)),
     (18, 2050, 5.0, 5.0, ("ladder", 4)),
+    # power-of-two grids whose padded y axis reaches 2048 / 4096: spectra and the admissibility plane through
+    # cosine transforms of the unmirrored grid (pfx_dct.cu), one and two parts per line
+    (16, 1024, 5.0, 5.0, ("ladder", 3)),
+    (8, 2048, 5.0, 5.0, ("ladder", 4)),
 ]
 
 
@@ -82,6 +86,26 @@ def test_fused_reductions_match_oracle(pf, ora, engine, nx, ny, dx, dy, kf):
     assert_maps_close(xs.real, rxs.real, "wl_xsg.real", atol_rel=1e-11)
     assert_maps_close(xs.imag, rxs.imag, "wl_xsg.imag", atol_rel=1e-11)
     assert_maps_close(exs, rexs, "ewl_xsg")
+
+
+@pytest.mark.parametrize("st,sg", [(1e-80, 1.0), (1.0, 1e-90), (1e80, 1e80), (1e-100, 1e-100)])
+def test_extreme_amplitudes_keep_the_reference_guard(pf, ora, st, sg):
+    """cpwt_sub.f90:329: the jackknife's guard is (p1 /= 0 .and. p2 /= 0), not "p1*p2 /= 0".  With grids so small or so
+    large that the product of the two running sums leaves the float64 range (powers below 1e-150 / above 1e150) the
+    epilogue switches, per cell, to the reference's guard and IEEE divisions formed without that product (in the
+    last case p1*p2 underflows to zero in every cell although neither sum is zero)."""
+    from plateflex_b200.cpwt import fused
+    nx, ny, dx, dy = 40, 36, 10.0, 10.0
+    t = red_field(nx, ny, seed=5) * 500.0 * st
+    g = (0.08 * red_field(nx, ny, seed=5) * 500.0 + red_field(nx, ny, seed=6) * 20.0) * sg
+    kf = np.array([1.5e-5, 4e-5, 1.2e-4])
+    w1 = ora.wlet_transform(t, dx, dy, kf, k0=pf.cf_wt.k0)
+    w2 = ora.wlet_transform(g, dx, dy, kf, k0=pf.cf_wt.k0)
+    with np.errstate(all="ignore"):
+        ref = ora.wlet_admit_coh(w1, w2)
+    for name, a, b in zip(("wl_admit", "ewl_admit", "wl_coh", "ewl_coh"), fused.wlet_admit_coh(t, g, dx, dy, kf), ref):
+        assert np.isfinite(b).any(), name
+        assert_maps_close(a, b, name)
 
 
 def test_scale_subrange(pf, ora, engine):
@@ -768,13 +792,15 @@ def test_two_gpu_pipeline_equals_single_gpu_bit_for_bit(pf):
 @pytest.mark.parametrize("knobs", [{"PLATEFLEX_B200_V3": "on"}, {"PLATEFLEX_B200_V3": "1", "PLATEFLEX_B200_V3_OCC": "2"},
                                    {"PLATEFLEX_B200_V3": "2", "PLATEFLEX_B200_V3_P1": "off"}, {"PLATEFLEX_B200_V2H": "on"},
                                    {"PLATEFLEX_B200_V4": "on"}, {"PLATEFLEX_B200_V4": "p2", "PLATEFLEX_B200_V4_WAVES": "2"},
-                                   {"PLATEFLEX_B200_V4": "off"}])
+                                   {"PLATEFLEX_B200_V4": "off"}, {"PLATEFLEX_B200_DCT": "off"},
+                                   {"PLATEFLEX_B200_DCT": "off", "PLATEFLEX_B200_V4": "off"}])
 @pytest.mark.parametrize("nx,ny,dx,dy,kf", CASES[5:])
 def test_third_generation_pass_kernels_match_oracle(pf, ora, monkeypatch, knobs, nx, ny, dx, dy, kf):
     """The opt-in bulk-copy (cp.async.bulk + mbarrier) pass kernels of pfx_pruned_v3.cuh: transposed intermediate,
     one / two line buffers, 2 or 3 CTAs per SM, with and without the third-generation pass 1; and the 128-thread
     form of the second-generation pass 2 (v2h); the radix-16 fourth generation (pfx_pruned_v4.cuh) for both passes
-    or pass 2 only, and switched off (second generation)."""
+    or pass 2 only, and switched off (second generation); the cosine-transform form of the spectra (pfx_dct.cu,
+    default on power-of-two grids) switched off, i.e. the padded complex forward transform."""
     from plateflex_b200 import _lib
     from plateflex_b200.cpwt import fused
     for name, value in knobs.items():
