@@ -294,6 +294,16 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_reduced[b], cudaEventDisableTiming);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) {
+            int lo = 0, hi = 0;  // pass 1 of the next scale takes SM slots as soon as pass-2 CTAs retire
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            e = cudaStreamCreateWithPriority(&pl->s_p1, cudaStreamNonBlocking, hi);
+        }
+        for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+            e = cudaEventCreateWithFlags(&pl->ev_t_ready[b], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_t_free[b], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_spec, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             set_error("stream / event creation failed: %s", cudaGetErrorString(e));
             return fail(PFX_ERR_CUDA);
@@ -338,6 +348,12 @@ int pfx_plan_destroy(pfx_plan *pl)
     plan_free_pruned(pl);
     if (pl->s_aux) cudaStreamDestroy(pl->s_aux);
     if (pl->s_copy) cudaStreamDestroy(pl->s_copy);
+    if (pl->s_p1) cudaStreamDestroy(pl->s_p1);
+    for (int b = 0; b < 2; b++) {
+        if (pl->ev_t_ready[b]) cudaEventDestroy(pl->ev_t_ready[b]);
+        if (pl->ev_t_free[b]) cudaEventDestroy(pl->ev_t_free[b]);
+    }
+    if (pl->ev_spec) cudaEventDestroy(pl->ev_spec);
     for (int b = 0; b < 2; b++) {
         if (pl->ev_planes[b]) cudaEventDestroy(pl->ev_planes[b]);
         if (pl->ev_reduced[b]) cudaEventDestroy(pl->ev_reduced[b]);
@@ -488,6 +504,20 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
     // (per-kernel timing serialises everything on the caller's stream so that event pairs time one kernel each)
     const bool overlap = nbuf == 2 && mode != OUT_CUBE && !pl->profiling;
     cudaStream_t red_stream = overlap ? pl->s_aux : pl->stream;
+    // pass 1 of scale n+1 on s_p1 while pass 2 of scale n runs (PLATEFLEX_B200_P1_AHEAD=off: one stream)
+    static const bool p1_ahead_on = [] {
+        const char *e = getenv("PLATEFLEX_B200_P1_AHEAD");
+        return !(e && !strcmp(e, "off"));
+    }();
+    const bool p1_ahead = overlap && pruned && p1_ahead_on;
+    const int nsc_call = is1 - is_base;
+    auto scale_at = [&](int n) { return scale_list ? scale_list[n] : is_base + n; };
+    if (p1_ahead) {
+        PFX_CUDA(cudaEventRecord(pl->ev_spec, pl->stream));  // spectra and Z are ready
+        PFX_CUDA(cudaStreamWaitEvent(pl->s_p1, pl->ev_spec, 0));
+        PFX_CHECK(pruned_pass1(pl, scale_at(0), ngrids, 0, pl->s_p1));
+        PFX_CUDA(cudaEventRecord(pl->ev_t_ready[0], pl->s_p1));
+    }
     for (int n = 0; n < is1 - is_base; n++) {
         const int is = scale_list ? scale_list[n] : is_base + n;  // n: position in this call's sequence
         const int b = n & 1;
@@ -503,7 +533,19 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
                 pruned_select_buffer(pl, b);
                 if (n >= 2) PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_reduced[b], 0));
             }
-            PFX_CHECK(pruned_scale_planes(pl, is, ngrids));
+            if (p1_ahead) {
+                PFX_CUDA(cudaStreamWaitEvent(pl->stream, pl->ev_t_ready[b], 0));
+                PFX_CHECK(pruned_pass2(pl, is, ngrids, b, pl->stream));
+                PFX_CUDA(cudaEventRecord(pl->ev_t_free[b], pl->stream));
+                if (n + 1 < nsc_call) {
+                    // T[b^1] was last read by pass 2 of scale n-1
+                    if (n >= 1) PFX_CUDA(cudaStreamWaitEvent(pl->s_p1, pl->ev_t_free[b ^ 1], 0));
+                    PFX_CHECK(pruned_pass1(pl, scale_at(n + 1), ngrids, b ^ 1, pl->s_p1));
+                    PFX_CUDA(cudaEventRecord(pl->ev_t_ready[b ^ 1], pl->s_p1));
+                }
+            } else {
+                PFX_CHECK(pruned_scale_planes(pl, is, ngrids));
+            }
             v1 = pruned_view(pl, 0);
             v2 = pruned_view(pl, ngrids - 1);
         }

@@ -154,7 +154,7 @@ struct PrunedState {
     double2 *rootx = nullptr, *rooty = nullptr;
     double *tabu = nullptr, *tabv = nullptr;
     double2 *twa = nullptr, *twb = nullptr;
-    double2 *T = nullptr, *W = nullptr, *Wbuf[2] = {nullptr, nullptr}, *zc = nullptr, *zplanes = nullptr;
+    double2 *T = nullptr, *Tbuf[2] = {nullptr, nullptr}, *W = nullptr, *Wbuf[2] = {nullptr, nullptr}, *zc = nullptr, *zplanes = nullptr;
     cufftHandle fft_z = 0;
     bool fft_z_ok = false;
     size_t smem1 = 0, smem2 = 0;
@@ -334,7 +334,8 @@ int plan_init_pruned(pfx_plan *pl)
     PFX_CHECK(dalloc((void **)&st->tabv, tabv_n * sizeof(double)));
     PFX_CHECK(dalloc((void **)&st->twa, twa_n * sizeof(double2)));
     PFX_CHECK(dalloc((void **)&st->twb, twb_n * sizeof(double2)));
-    PFX_CHECK(dalloc((void **)&st->T, 2 * PFX_NA * t_elems * sizeof(double2)));
+    for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Tbuf[b], 2 * PFX_NA * t_elems * sizeof(double2)));
+    st->T = st->Tbuf[0];
     for (int b = 0; b < 2; b++) PFX_CHECK(dalloc((void **)&st->Wbuf[b], 2 * PFX_NA * (size_t)nx * ny * sizeof(double2)));
     st->W = st->Wbuf[0];
     PFX_CHECK(dalloc((void **)&st->zc, (size_t)nx * ny * sizeof(double2)));
@@ -516,14 +517,14 @@ int pruned_prepare(pfx_plan *pl, int ngrids)
     return PFX_OK;
 }
 
-int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
+namespace {
+// kernel arguments of scale `is` with intermediate buffer tb
+int scale_args(pfx_plan *pl, PrunedState *st, int is, int ngrids, int tb, PrunedArgs &a)
 {
-    PrunedState *st = state_of(pl);
     if (!st) {
         set_error("pruned engine not initialised");
         return PFX_ERR_STATE;
     }
-    PrunedArgs a;
     a.sd = st->sd[is];
     a.nx = pl->nx;
     a.ny = pl->ny;
@@ -544,61 +545,80 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
     a.twb = st->twb;
     a.rootx = st->rootx;
     a.rooty = st->rooty;
-    a.T = st->T;
+    a.T = st->Tbuf[tb & 1];
     a.W = st->W;
     if (st->v3x_nbuf[is]) {
         a.t_tr = 1;
         a.t_lp = v3_line_slots(a.sd.ax.logL);
         a.t_pad = v3_pad(a.sd.ax.logL);
     }
+    return PFX_OK;
+}
+}  // namespace
+
+int pruned_pass1(pfx_plan *pl, int is, int ngrids, int tb, cudaStream_t stream)
+{
+    PrunedState *st = state_of(pl);
+    PrunedArgs a;
+    PFX_CHECK(scale_args(pl, st, is, ngrids, tb, a));
     const ScaleDesc &sd = a.sd;
-    const size_t sm1 = prn_smem_bytes(sd.ay, 1), sm2 = prn_smem_bytes(sd.ax, st->cpc);
-    const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
+    const size_t sm1 = prn_smem_bytes(sd.ay, 1);
     dim3 g1(std::min(sd.kamax, st->ctas_per_transform), PFX_NA * ngrids);
+    const int ntr = PFX_NA * ngrids;
+    const char *ctas_env = getenv("PLATEFLEX_B200_CTAS");
+    NvtxRange r("pfx:pass1");
+    ProfScope prof(pl, PFX_KC_PASS1, stream);
+    if (st->v4y_ctas[is]) {
+        v4::V4Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
+        const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v4y_ctas[is] / ntr);
+        PFX_CHECK(v4_launch_p1(va, sd.ay.logL, sd.ay.N > 2048, st->dct != nullptr, dim3(std::min(sd.kamax, ctas), ntr), stream));
+    } else if (st->v3y_nbuf[is]) {
+        const int multi = (st->v2y[is] >> 5) & 1;
+        v3::V3Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1), st->v3y_nbuf[is]};
+        // a few waves: the number of columns differs between azimuths
+        const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v3y_ctas[is] / ntr);
+        PFX_CHECK(v3_launch_p1(va, sd.ay.logL, multi, 2 * pl->ny == pl->NY, st->v3_occ, dim3(std::min(sd.kamax, ctas), ntr), stream));
+    } else if (st->v2y[is] >= 0) {
+        v2::V2Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
+        const int cpc = st->v2y[is] & 15, groups = (sd.kamax + cpc - 1) / cpc;
+        // a few waves: the number of columns differs between azimuths
+        const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v2y_ctas[is] / ntr);
+        PFX_CHECK(v2_launch_p1(va, sd.ay.logL, st->v2y[is], dim3(std::min(groups, ctas), ntr), stream));
+    } else {
+        PFX_CHECK(prn_launch_pass1(a, g1, sm1, stream));
+    }
+    pl->launches += 1;
+    return PFX_OK;
+}
+
+int pruned_pass2(pfx_plan *pl, int is, int ngrids, int tb, cudaStream_t stream)
+{
+    PrunedState *st = state_of(pl);
+    PrunedArgs a;
+    PFX_CHECK(scale_args(pl, st, is, ngrids, tb, a));
+    const ScaleDesc &sd = a.sd;
+    const size_t sm2 = prn_smem_bytes(sd.ax, st->cpc);
+    const int ngroups = (pl->ny + st->cpc - 1) / st->cpc;
     dim3 g2(std::min(ngroups, st->ctas_per_transform), PFX_NA * ngrids);
     const int ntr = PFX_NA * ngrids;
     const char *ctas_env = getenv("PLATEFLEX_B200_CTAS");
     {
-        NvtxRange r("pfx:pass1");
-        ProfScope prof(pl, PFX_KC_PASS1, pl->stream);
-        if (st->v4y_ctas[is]) {
-            v4::V4Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
-            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v4y_ctas[is] / ntr);
-            PFX_CHECK(v4_launch_p1(va, sd.ay.logL, sd.ay.N > 2048, st->dct != nullptr, dim3(std::min(sd.kamax, ctas), ntr), pl->stream));
-        } else if (st->v3y_nbuf[is]) {
-            const int multi = (st->v2y[is] >> 5) & 1;
-            v3::V3Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1), st->v3y_nbuf[is]};
-            // a few waves: the number of columns differs between azimuths
-            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v3y_ctas[is] / ntr);
-            PFX_CHECK(v3_launch_p1(va, sd.ay.logL, multi, 2 * pl->ny == pl->NY, st->v3_occ, dim3(std::min(sd.kamax, ctas), ntr),
-                                   pl->stream));
-        } else if (st->v2y[is] >= 0) {
-            v2::V2Args va{a, sd.ay.logr, std::max(sd.ay.N >> 11, 1)};
-            const int cpc = st->v2y[is] & 15, groups = (sd.kamax + cpc - 1) / cpc;
-            // a few waves: the number of columns differs between azimuths
-            const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, 3 * st->v2y_ctas[is] / ntr);
-            PFX_CHECK(v2_launch_p1(va, sd.ay.logL, st->v2y[is], dim3(std::min(groups, ctas), ntr), pl->stream));
-        } else {
-            PFX_CHECK(prn_launch_pass1(a, g1, sm1, pl->stream));
-        }
-    }
-    {
         NvtxRange r("pfx:pass2");
-        ProfScope prof(pl, PFX_KC_PASS2, pl->stream);
+        ProfScope prof(pl, PFX_KC_PASS2, stream);
         if (st->v4x_ctas[is]) {
             v4::V4Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
             const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v4_waves_p2 * st->v4x_ctas[is] / ntr);
-            PFX_CHECK(v4_launch_p2(va, sd.ax.logL, sd.ax.N > 2048, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+            PFX_CHECK(v4_launch_p2(va, sd.ax.logL, sd.ax.N > 2048, dim3(std::min(pl->ny, ctas), ntr), stream));
         } else if (st->v3x_nbuf[is]) {
             const int multi = (st->v2x[is] >> 5) & 1;
             v3::V3Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1), st->v3x_nbuf[is]};
             // every transform has the same number of rows: one wave of persistent CTAs
             const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v3x_ctas[is] / ntr);
-            PFX_CHECK(v3_launch_p2(va, sd.ax.logL, multi, 2 * pl->nx == pl->NX, st->v3_occ, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+            PFX_CHECK(v3_launch_p2(va, sd.ax.logL, multi, 2 * pl->nx == pl->NX, st->v3_occ, dim3(std::min(pl->ny, ctas), ntr), stream));
         } else if (st->v2hx_ctas[is]) {
             v2h::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 10, 1)};
             const int ctas = ctas_env ? st->ctas_per_transform : std::max(1, st->v2hx_ctas[is] / ntr);
-            PFX_CHECK(v2h_launch_p2(va, sd.ax.logL, sd.ax.N > 1024, dim3(std::min(pl->ny, ctas), ntr), pl->stream));
+            PFX_CHECK(v2h_launch_p2(va, sd.ax.logL, sd.ax.N > 1024, dim3(std::min(pl->ny, ctas), ntr), stream));
         } else if (st->v2x[is] >= 0) {
             v2::V2Args va{a, sd.ax.logr, std::max(sd.ax.N >> 11, 1)};
             const int cpc = st->v2x[is] & 15, groups = (pl->ny + cpc - 1) / cpc;
@@ -607,26 +627,37 @@ int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
             // faster than one wave (the rows of a CTA stay closer together, the tail is finer)
             const bool multi = (st->v2x[is] >> 5) & 1;
             const int ctas = ctas_env ? st->ctas_per_transform : (multi ? 192 : std::max(1, st->v2x_ctas[is] / ntr));
-            PFX_CHECK(v2_launch_p2(va, sd.ax.logL, st->v2x[is], dim3(std::min(groups, ctas), ntr), pl->stream));
+            PFX_CHECK(v2_launch_p2(va, sd.ax.logL, st->v2x[is], dim3(std::min(groups, ctas), ntr), stream));
         } else {
-            PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, pl->stream));
+            PFX_CHECK(prn_launch_pass2(a, st->cpc, g2, sm2, stream));
         }
     }
     for (int ia = 0; ia < PFX_NA; ia++) st->cur_ce[ia] = sd.ce[ia];
-    pl->launches += 2;
+    pl->launches += 1;
     return PFX_OK;
 }
 
-// Relative cost model of one scale (arbitrary units ~ microseconds on B200), fitted to the measured kernel
-// times of the 1024^2 configuration: both passes scale with lines x line length x log2(FFT length),
-// the reduction with the number of cells.  Used to balance scale blocks over ranks.
+int pruned_scale_planes(pfx_plan *pl, int is, int ngrids)
+{
+    PFX_CHECK(pruned_pass1(pl, is, ngrids, 0, pl->stream));
+    return pruned_pass2(pl, is, ngrids, 0, pl->stream);
+}
+
+// Relative cost model of one scale (arbitrary units ~ microseconds on B200), from the measured launch times of the
+// 4096^2 configuration (profiles/r02_launch_summary.txt, radix-16 pass 2): pass 2 scales with rows x line length
+// times a factor per FFT length (1.96 ms at L = 32 ... 4.58 ms at L = 2048 for 4096 x 8192 x 22), pass 1 with
+// columns x line length x log2(FFT length), the reduction with the number of cells.  Used to balance scales over
+// ranks (sharding.deal_scales / balanced_cuts).
 double pruned_scale_cost(const pfx_plan *pl, int is)
 {
     const PrunedState *st = reinterpret_cast<const PrunedState *>(pl->pruned);
     const ScaleDesc &sd = st->sd[is];
-    const double p2 = (double)pl->ny * pl->NX * sd.ax.logL * (sd.ax.logL >= 10 ? 1.4 : 1.0);
-    const double p1 = (double)sd.kamax * pl->NY * sd.ay.logL;
-    return 1.6e-5 * (p1 + p2) + 1.0e-4 * (double)pl->nx * pl->ny;
+    static const double p2_ms[7] = {1.96, 2.00, 2.17, 2.69, 2.93, 3.41, 4.58};  // logL = 5 .. 11
+    const int l = sd.ax.logL;
+    const double per = l < 5 ? p2_ms[0] : (l > 11 ? p2_ms[6] * (double)l / 11.0 : p2_ms[l - 5]);
+    const double p2 = per * 1e3 * ((double)pl->ny * pl->NX) / (4096.0 * 8192.0);
+    const double p1 = 1.4e-5 * (double)sd.kamax * pl->NY * sd.ay.logL;
+    return p1 + p2 + 0.8e-4 * (double)pl->nx * pl->ny;
 }
 
 int pruned_num_buffers(const pfx_plan *pl) { return pl->pruned ? 2 : 1; }

@@ -618,8 +618,11 @@ __device__ __forceinline__ double rcp_nr(double x)
 // exp(-k*(zc+wd)), exp(-k*wd) are kept per thread in shared memory.  No lane ever idles on the
 // small dense algebra of the optimiser, which made this 3x cheaper than one warp per cell.
 constexpr int FIT_NT = 128;
+#ifndef FIT_PAIR
+#define FIT_PAIR 1  // lane kernel: two scales side by side in the model loop (P2 of pfx_flex.cuh)
+#endif
 #ifndef FIT_UNROLL
-#define FIT_UNROLL 2  // scales evaluated side by side in the model loop (independent dependency chains)
+#define FIT_UNROLL (FIT_PAIR ? 1 : 2)  // unrolling of the model loop over scales (pairs of scales with FIT_PAIR)
 #endif
 constexpr int FIT_UNROLL_N = FIT_UNROLL;
 #ifndef FIT_MIN_BLOCKS
@@ -813,22 +816,21 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
         double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
         for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
-#pragma unroll FIT_UNROLL_N
-        for (int s = 0; s < a.ns; s++) {
-            FlexK fk;
-            fk.k4d = k4[s];
-            fk.deep = sdeep[s * FIT_NT + tid];
-            fk.top = 0.;
+        // the depth factors of scale s (see the fetch below for the three storage forms)
+        auto depth = [&](int s, double &top, double &deep) {
+            deep = sdeep[s * FIT_NT + tid];
+            top = 0.;
             if (freeair) {
                 if (two) {
-                    fk.top = stop[s * FIT_NT + tid];
+                    top = stop[s * FIT_NT + tid];
                 } else {
-                    fk.top = ctop * fk.deep;
-                    fk.deep = cdeep * (ezc[s] * fk.deep);
+                    top = ctop * deep;
+                    deep = cdeep * (ezc[s] * deep);
                 }
             }
-            double adm, coh, dA[3], dC[3];
-            flex_eval<true>(fc, fk, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+        };
+        // one residual row per observable of scale s, in the order admittance, coherence
+        auto rows = [&](int s, double adm, double coh, const double(&dA)[3], const double(&dC)[3]) {
             if (use_adm) {
                 const double w = sobs[(1 * a.ns + s) * FIT_NT + tid];  // curve_fit: transform = 1/sigma
                 const double r = (adm - sobs[(0 * a.ns + s) * FIT_NT + tid]) * w;
@@ -845,7 +847,38 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
                 for (int p = 0; p < NP; p++) jr[p] = dC[p] * w;
                 accumulate<NP>(acc, r, jr);
             }
+        };
+#if FIT_PAIR
+        // two scales side by side (pfx_flex.cuh, P2): independent chains for the FP64 pipe; rows accumulated in
+        // scale order, so the sums are those of the one-scale loop
+        int s = 0;
+#pragma unroll FIT_UNROLL_N
+        for (; s + 1 < a.ns; s += 2) {
+            P2 k4d = {k4[s], k4[s + 1]}, top, deep;
+            depth(s, top.a, deep.a);
+            depth(s + 1, top.b, deep.b);
+            P2 adm, coh, dA[3], dC[3];
+            flex_eval_g<true, P2>(fc, k4d, top, deep, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+            const double dAa[3] = {dA[0].a, dA[1].a, dA[2].a}, dCa[3] = {dC[0].a, dC[1].a, dC[2].a};
+            const double dAb[3] = {dA[0].b, dA[1].b, dA[2].b}, dCb[3] = {dC[0].b, dC[1].b, dC[2].b};
+            rows(s, adm.a, coh.a, dAa, dCa);
+            rows(s + 1, adm.b, coh.b, dAb, dCb);
         }
+        if (s < a.ns) {
+            double top, deep, adm, coh, dA[3], dC[3];
+            depth(s, top, deep);
+            flex_eval_g<true, double>(fc, k4[s], top, deep, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+            rows(s, adm, coh, dA, dC);
+        }
+#else
+#pragma unroll FIT_UNROLL_N
+        for (int s = 0; s < a.ns; s++) {
+            double top, deep, adm, coh, dA[3], dC[3];
+            depth(s, top, deep);
+            flex_eval_g<true, double>(fc, k4[s], top, deep, te, te3, ff, dff, ca, sa, adm, coh, dA, dC);
+            rows(s, adm, coh, dA, dC);
+        }
+#endif
         unpack<NP>(acc, nm);
     };
 

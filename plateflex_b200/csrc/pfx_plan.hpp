@@ -68,6 +68,10 @@ struct pfx_plan {
     // scales to the host on s_copy.  Everything is joined back into `stream` before a call returns.
     cudaStream_t s_aux = nullptr, s_copy = nullptr;
     cudaEvent_t ev_planes[2] = {nullptr, nullptr}, ev_reduced[2] = {nullptr, nullptr}, ev_join = nullptr;
+    // Pruned engine: pass 1 of scale s+1 (short, latency-bound launches) runs on s_p1 while pass 2 of scale s runs
+    // on the caller's stream; two intermediate buffers T, guarded by these events
+    cudaStream_t s_p1 = nullptr;
+    cudaEvent_t ev_t_ready[2] = {nullptr, nullptr}, ev_t_free[2] = {nullptr, nullptr}, ev_spec = nullptr;
 
     // grow-only scratch used by the _host entry points (inputs / outputs staging)
     void *d_scratch[10] = {};
@@ -134,6 +138,9 @@ int pruned_prepare(pfx_plan *pl, int ngrids);          // admissibility transfor
 // grids, else forward_spectrum
 int pruned_forward(pfx_plan *pl, const double *grid_dev, int slot);
 int pruned_scale_planes(pfx_plan *pl, int is, int ngrids);  // -> compact W planes of scale `is`
+// the two halves of pruned_scale_planes on a chosen stream and intermediate buffer tb (0 | 1)
+int pruned_pass1(pfx_plan *pl, int is, int ngrids, int tb, cudaStream_t stream);
+int pruned_pass2(pfx_plan *pl, int is, int ngrids, int tb, cudaStream_t stream);
 PlaneView pruned_view(const pfx_plan *pl, int g);
 int pruned_num_buffers(const pfx_plan *pl);
 double pruned_scale_cost(const pfx_plan *pl, int is);
