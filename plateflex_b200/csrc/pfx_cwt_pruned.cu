@@ -78,40 +78,40 @@ __global__ void twiddle_kernel(int logN, int logL, const int *lo, const double2 
 }
 
 // Admissibility term on the y-fastest layout (cpwt_sub.f90:93).  exp(-kx^2/2) exp(-ky^2/2) is real and even and
-// the spectra of the (real) grids are Hermitian, so the transform of the product is real: both grids share ONE
-// complex plane,  plane[a][b] = G (X_0 + i X_1)[a][b],  whose inverse transform is Z_0 + i Z_1.
-__global__ void zmul_kernel(int NX, int NY, const double2 *__restrict__ s0, const double2 *__restrict__ s1,
-                            const double *__restrict__ u2, const double *__restrict__ v2, double2 *plane)
+// the spectrum of a (real) grid is Hermitian, so the transform of the product is real.  One plane per grid: packing
+// both grids into one complex transform (X_0 + i X_1) would halve the work but ties the rounding error of each
+// plane to the amplitude of the larger one -- with grids in very different units (topography in metres, gravity
+// in m/s^2: seven orders of magnitude) that eats the 1e-9 budget of the smaller one.
+__global__ void zmul_kernel(int NX, int NY, const double2 *__restrict__ s0, const double *__restrict__ u2,
+                            const double *__restrict__ v2, double2 *plane)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
     if (b >= NY) return;
     const size_t o = (size_t)a * NY + b;
     const double w = u2[a] * v2[b];
-    double2 x = s0[o];
-    if (s1) {
-        const double2 x1 = s1[o];
-        x = make_double2(x.x - x1.y, x.y + x1.x);
-    }
+    const double2 x = s0[o];
     plane[o] = make_double2(w * x.x, w * x.y);
 }
 
-// zc[j][i] = scale * plane[i+1][j+1] = (Z_0, Z_1)(i, j): crop with the one-sample shift, transposed to the
-// x-fastest layout of the coefficient planes through a 32 x 32 shared-memory tile
+// zc[j][i].{x|y} = scale * Re plane[i+1][j+1] = Z_g(i, j) (comp = g): crop with the one-sample shift, transposed to
+// the x-fastest layout of the coefficient planes through a 32 x 32 shared-memory tile; `clear` zeroes the other
+// component (single-grid calls)
 __global__ void __launch_bounds__(256)
-    zcrop_kernel(int nx, int ny, int NY, double scale, const double2 *__restrict__ plane, double2 *zc)
+    zcrop_kernel(int nx, int ny, int NY, double scale, const double2 *__restrict__ plane, double2 *zc, int comp, int clear)
 {
-    __shared__ double2 tile[32][33];
+    __shared__ double tile[32][33];
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int i = i0 + r, j = j0 + threadIdx.x;
-        if (i < nx && j < ny) tile[r][threadIdx.x] = plane[(size_t)(i + 1) * NY + (j + 1)];
+        if (i < nx && j < ny) tile[r][threadIdx.x] = plane[(size_t)(i + 1) * NY + (j + 1)].x;
     }
     __syncthreads();
     for (int c = threadIdx.y; c < 32; c += 8) {
         const int i = i0 + threadIdx.x, j = j0 + c;
         if (i < nx && j < ny) {
-            const double2 v = tile[threadIdx.x][c];
-            zc[(size_t)j * nx + i] = make_double2(v.x * scale, v.y * scale);
+            double *z = reinterpret_cast<double *>(zc + (size_t)j * nx + i);
+            z[comp] = tile[threadIdx.x][c] * scale;
+            if (clear) z[comp ^ 1] = 0.0;
         }
     }
 }
@@ -504,16 +504,18 @@ int pruned_prepare(pfx_plan *pl, int ngrids)
     if (st->dct) return dct_prepare(pl, st->dct, ngrids, st->zc);
     const size_t P = (size_t)pl->NX * pl->NY;
     ProfScope prof(pl, PFX_KC_PREPARE, pl->stream);
-    zmul_kernel<<<dim3((pl->NY + 255) / 256, pl->NX), 256, 0, pl->stream>>>(
-        pl->NX, pl->NY, pl->d_spec[0], ngrids == 2 ? pl->d_spec[1] : nullptr, pl->d_u2, pl->d_v2, st->zplanes);
-    PFX_CUDA(cudaGetLastError());
     cufftHandle h = st->fft_z;
     PFX_CUFFT(cufftSetStream(h, pl->stream));
-    PFX_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *)st->zplanes, (cufftDoubleComplex *)st->zplanes, CUFFT_INVERSE));
-    zcrop_kernel<<<dim3((pl->nx + 31) / 32, (pl->ny + 31) / 32), dim3(32, 8), 0, pl->stream>>>(
-        pl->nx, pl->ny, pl->NY, 1.0 / (double)P, st->zplanes, st->zc);
-    PFX_CUDA(cudaGetLastError());
-    pl->launches += 3;
+    for (int g = 0; g < ngrids; g++) {
+        zmul_kernel<<<dim3((pl->NY + 255) / 256, pl->NX), 256, 0, pl->stream>>>(pl->NX, pl->NY, pl->d_spec[g], pl->d_u2,
+                                                                                pl->d_v2, st->zplanes);
+        PFX_CUDA(cudaGetLastError());
+        PFX_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex *)st->zplanes, (cufftDoubleComplex *)st->zplanes, CUFFT_INVERSE));
+        zcrop_kernel<<<dim3((pl->nx + 31) / 32, (pl->ny + 31) / 32), dim3(32, 8), 0, pl->stream>>>(
+            pl->nx, pl->ny, pl->NY, 1.0 / (double)P, st->zplanes, st->zc, g, ngrids == 1);
+        PFX_CUDA(cudaGetLastError());
+    }
+    pl->launches += 3 * ngrids;
     return PFX_OK;
 }
 

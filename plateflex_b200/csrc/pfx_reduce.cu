@@ -72,12 +72,12 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
 
 // cpwt_sub.f90:329-335: co = Re(xp)^2/(p1*p2), ad = Re(xp)/p1, both 0 when a sum is 0 -- added straight into the
 // running sums of the walk (sa += ad, sc += co).
-// FAST (every non-zero per-azimuth power of the cell lies in [1e-150, 1e150], checked once per cell by the caller,
-// so no prefix product can underflow or overflow): one branch-free reciprocal serves both quotients
+// FAST (every per-azimuth power of the cell is a normal number in [1e-150, 1e150], checked once per cell by the
+// caller on the high words, so no prefix product can underflow or overflow): one branch-free reciprocal serves both quotients
 // (ad = xp*p2/(p1*p2)) with one fused multiply-add each; the sums are non-negative, so "a sum is 0" is "the
 // product is 0", read from its exponent and mantissa bits with integer instructions; results differ from the
 // reference's IEEE divisions by a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
-// Otherwise (grids of extreme amplitude): the reference's own guard (p1 /= 0 .and. p2 /= 0) and IEEE divisions,
+// Otherwise (grids of extreme amplitude, exact zeros): the reference's own guard (p1 /= 0 .and. p2 /= 0) and IEEE divisions,
 // formed as (xp/p1)*(xp/p2) so that the product of the two sums is never taken.
 template <bool FAST>
 __device__ __forceinline__ void ratio_acc(double q1, double q2, double qx, double &sa, double &sc)
@@ -136,13 +136,9 @@ __device__ __noinline__ void jk_admit_coh_exact(const JkTriples t, double *ead, 
     jk_admit_coh<false>(t.s1, t.s2, t.xr, *ead, *eco);
 }
 
-// non-zero and outside [1e-150, 1e150] (or not finite): high word of the double against the two exponents
-__device__ __forceinline__ bool extreme(double v)
-{
-    const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu;
-    const bool zero = (hi | (unsigned)__double2loint(v)) == 0u;
-    return !zero && (hi < 0x20ca2fe7u || hi > 0x5f138d35u);  // 1e-150 = 0x20ca2fe76a3f9475, 1e150 = 0x5f138d352e5096af
-}
+// High words of the doubles 1e-150 and 1e150: a power whose high word lies in [LO, HI] is a normal number in
+// [1e-150, 1e150] (zeros, subnormals, huge values, infinities and NaNs all fall outside)
+constexpr int PW_HI_LO = 0x20ca2fe8, PW_HI_HI = 0x5f138d34;
 
 // the (real) admissibility terms of both grids at cell (i, j)
 __device__ __forceinline__ double2 load_z(const PlaneView &v, int i, int j)
@@ -218,23 +214,32 @@ __global__ void __launch_bounds__(128, OCC)
     } else {
         double s1[NA], s2[NA], xr[NA];
         double t1 = 0.0, t2 = 0.0, tx = 0.0;
-        bool odd = false;
+        int hmin = 0x7fffffff, hmax = 0;  // range of the high words of the 22 powers (non-negative doubles)
 #pragma unroll
         for (int a = 0; a < NA; a++) {
             const double2 u = load_w(w1, a, i, j, z1), v = load_w(w2, a, i, j, z2);
             s1[a] = fabs(u.x * u.x + u.y * u.y);  // cpwt.f90:333
             s2[a] = fabs(v.x * v.x + v.y * v.y);  // cpwt.f90:334
             xr[a] = u.x * v.x + u.y * v.y;        // Re(w1*CONJG(w2)), cpwt.f90:335
-            odd = odd || extreme(s1[a]) || extreme(s2[a]);
+#ifndef PFX_RED_NOCHECK
+            hmin = min(hmin, min(__double2hiint(s1[a]), __double2hiint(s2[a])));
+            hmax = max(hmax, max(__double2hiint(s1[a]), __double2hiint(s2[a])));
+#endif
             t1 += s1[a];
             t2 += s2[a];
             tx += xr[a];
         }
+        // a power that is zero, subnormal, beyond [1e-150, 1e150] or not finite: the cell takes the exact path
+#ifndef PFX_RED_NOCHECK
+        const bool odd = hmin < PW_HI_LO || hmax > PW_HI_HI;
+#else
+        const bool odd = false;
+#endif
         t1 = t1 * (1.0 / (double)NA);  // cpwt.f90:348-350
         t2 = t2 * (1.0 / (double)NA);
         tx = tx * (1.0 / (double)NA);
         put<F32>(out0, o, tx / t1);                                            // cpwt.f90:354
-        put<F32>(out2, o, odd ? (tx / t1) * (tx / t2) : (tx * tx) / (t1 * t2));  // cpwt.f90:355
+        put<F32>(out2, o, (tx * tx) / (t1 * t2));                              // cpwt.f90:355
         double ead, eco;
         if (odd) {
             JkTriples t;
