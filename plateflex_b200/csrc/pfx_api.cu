@@ -281,6 +281,7 @@ int pfx_plan_create(pfx_plan **out, int nx, int ny, double dx_km, double dy_km, 
     if ((rc = pl->alloc((void **)&pl->d_u2, pl->NX * sizeof(double)))) return fail(rc);
     if ((rc = pl->alloc((void **)&pl->d_v2, pl->NY * sizeof(double)))) return fail(rc);
     if ((rc = pl->alloc((void **)&pl->d_partial, 512 * sizeof(double)))) return fail(rc);
+    if ((rc = pl->alloc((void **)&pl->d_flag_words, 2 * sizeof(int)))) return fail(rc);
     // the pruned engine allocates the padded spectra itself unless it can use the cosine-transform form (pfx_dct.cu)
     if (engine != PFX_ENGINE_PRUNED)
         for (int g = 0; g < 2; g++)
@@ -568,7 +569,7 @@ int run_cwt(pfx_plan *pl, int mode, const double *g1, const double *g2, int is0,
                 sh.scale = is;
             }
             PFX_CHECK(launch_reduce(mode, pl->nx, pl->ny, v1, v2, o[0], o[1], o[2], o[3], red_stream, shards ? &sh : nullptr,
-                                    d32 != nullptr));
+                                    d32 != nullptr, pl->d_flag_words + b));
         }
         pl->launches++;
         if (overlap || h_outs || h32) PFX_CUDA(cudaEventRecord(pl->ev_reduced[b], red_stream));

@@ -100,7 +100,11 @@ struct ShardOut {
 //   RED_ADMIT_COH : w1,w2 -> out0..3 = wl_admit, ewl_admit, wl_coh, ewl_coh (cpwt.f90:303-364)
 // Each out* points at the (nx, ny) plane of this scale (x fastest); with f32 they are float arrays.
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream, const ShardOut *shards = nullptr, bool f32 = false);
+                  double *out3, cudaStream_t stream, const ShardOut *shards = nullptr, bool f32 = false,
+                  int *flag_word = nullptr);
+// flag_word (RED_ADMIT_COH): a device int owned by the caller that no other launch in flight uses -- the "some cell
+// needs the exact jackknife" word shared by the kernel and its fix-up pass; when null one is allocated and freed in
+// stream order.
 
 // Copies between the device and pageable host memory through pinned chunks and a thread team (pfx_hostio.cu)
 bool host_is_pageable(const void *p);

@@ -22,6 +22,7 @@
 //   fit_cell_kernel  (PLATEFLEX_B200_FIT=static) one cell per thread per grid-stride trip;
 //                    also the fallback when the shared-memory cache does not fit
 //   fit_kernel       (PLATEFLEX_B200_FIT=group) G lanes per cell, scales strided over the lanes
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +63,7 @@ struct FitArgs {
     unsigned long long *todo_count = nullptr;
     int todo_cap = 0, trial_cap = 0;
     int finisher = 0;  // fit_kernel: take the cells from todo[0 .. min(*todo_count, todo_cap))
+    const int *dry_flag = nullptr;  // lane kernel: device word, 1 = no water anywhere and one crustal thickness
 };
 
 template <int NP>
@@ -618,6 +620,7 @@ __device__ __forceinline__ double rcp_nr(double x)
 // exp(-k*(zc+wd)), exp(-k*wd) are kept per thread in shared memory.  No lane ever idles on the
 // small dense algebra of the optimiser, which made this 3x cheaper than one warp per cell.
 constexpr int FIT_NT = 128;
+constexpr int FIT_NT_DRY = 64, FIT_CTAS_DRY = 5;  // the dry-land form of the lane kernel (see fit_lane_kernel)
 #ifndef FIT_PAIR
 #define FIT_PAIR 1  // lane kernel: two scales side by side in the model loop (P2 of pfx_flex.cuh)
 #endif
@@ -760,19 +763,26 @@ __global__ void __launch_bounds__(FIT_NT, CACHE ? 2 : FIT_MIN_BLOCKS) fit_cell_k
 // cell from a global counter (one atomic per warp and trip).  The arithmetic of a cell is the sequence of
 // trf_minimize exactly -- the outer-iteration quantities are recomputed from (x, J^T J, J^T r) on a retry
 // instead of being kept, which gives the same values -- so results do not depend on the schedule.
-template <int NP>
-__global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
+template <int NP, bool DRY>
+__global__ void __launch_bounds__(DRY ? FIT_NT_DRY : FIT_NT, DRY ? FIT_CTAS_DRY : 2) fit_lane_kernel(FitArgs a)
 {
+    // DRY: no cell of this launch lies under water and the crustal thickness is one number, so the depth factors of
+    // a scale are the same for every cell, e^{-k zc} (the table ezc), and no per-lane array of them is kept: 640
+    // instead of 800 bytes of shared memory per lane, ten warps per SM instead of eight -- the kernel is bound by
+    // the latency of the optimiser's dependent chains, so resident warps are what it needs.  a.dry_flag (device, set
+    // by wet_kernel before the launch) says which of the two variants of this launch does the work.
+    constexpr int LNT = DRY ? FIT_NT_DRY : FIT_NT;
+    if ((*a.dry_flag != 0) != DRY) return;
     extern __shared__ double fsh[];
     const bool freeair = a.conf.boug != 1;
     const bool two = freeair && a.zc_map != nullptr;  // both attenuation terms stored
     const bool shared_zc = freeair && !two;           // e^{-k wd} stored
     double *k4 = fsh;                              // [ns] k^4 * Em*1e9/12/(1-nu^2)
     double *ezc = fsh + a.ns;                      // [ns] e^{-k zc}  (uniform zc)
-    double *sdeep = fsh + 2 * a.ns;                // [ns][FIT_NT]
-    double *stop = sdeep + (size_t)a.ns * FIT_NT;  // [ns][FIT_NT]  (zc grid and free air only, else absent)
-    double *sobs = stop + (two ? (size_t)a.ns * FIT_NT : 0);  // [4][ns][FIT_NT] = adm, 1/eadm, coh, 1/ecoh
-    for (int s = threadIdx.x; s < a.ns; s += FIT_NT) {
+    double *sdeep = fsh + 2 * a.ns;                // [ns][LNT]  (absent when DRY)
+    double *stop = sdeep + (DRY ? 0 : (size_t)a.ns * LNT);  // [ns][LNT]  (zc grid and free air only, else absent)
+    double *sobs = stop + (two ? (size_t)a.ns * LNT : 0);  // [4][ns][LNT] = adm, 1/eadm, coh, 1/ecoh
+    for (int s = threadIdx.x; s < a.ns; s += LNT) {
         const double k2 = a.k[s] * a.k[s];
         k4[s] = (k2 * k2) * (FLEX_EM * 1.e9 / 12. / (1. - FLEX_NU * FLEX_NU));
         ezc[s] = exp(-a.k[s] * a.conf.zc);
@@ -818,11 +828,21 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
         for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
         // the depth factors of scale s (see the fetch below for the three storage forms)
         auto depth = [&](int s, double &top, double &deep) {
-            deep = sdeep[s * FIT_NT + tid];
+            if (DRY) {  // the values the general form stores for wd = 0, in the same order of operations
+                if (freeair) {
+                    top = ctop * 1.;
+                    deep = cdeep * (ezc[s] * 1.);
+                } else {
+                    top = 0.;
+                    deep = 2. * FLEX_PI * FLEX_GC * (fc.drho * ezc[s]);  // flex_k with wd = 0, zc = conf.zc
+                }
+                return;
+            }
+            deep = sdeep[s * LNT + tid];
             top = 0.;
             if (freeair) {
                 if (two) {
-                    top = stop[s * FIT_NT + tid];
+                    top = stop[s * LNT + tid];
                 } else {
                     top = ctop * deep;
                     deep = cdeep * (ezc[s] * deep);
@@ -832,16 +852,16 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
         // one residual row per observable of scale s, in the order admittance, coherence
         auto rows = [&](int s, double adm, double coh, const double(&dA)[3], const double(&dC)[3]) {
             if (use_adm) {
-                const double w = sobs[(1 * a.ns + s) * FIT_NT + tid];  // curve_fit: transform = 1/sigma
-                const double r = (adm - sobs[(0 * a.ns + s) * FIT_NT + tid]) * w;
+                const double w = sobs[(1 * a.ns + s) * LNT + tid];  // curve_fit: transform = 1/sigma
+                const double r = (adm - sobs[(0 * a.ns + s) * LNT + tid]) * w;
                 double jr[NP];
 #pragma unroll
                 for (int p = 0; p < NP; p++) jr[p] = dA[p] * w;
                 accumulate<NP>(acc, r, jr);
             }
             if (use_coh) {
-                const double w = sobs[(3 * a.ns + s) * FIT_NT + tid];
-                const double r = (coh - sobs[(2 * a.ns + s) * FIT_NT + tid]) * w;
+                const double w = sobs[(3 * a.ns + s) * LNT + tid];
+                const double r = (coh - sobs[(2 * a.ns + s) * LNT + tid]) * w;
                 double jr[NP];
 #pragma unroll
                 for (int p = 0; p < NP; p++) jr[p] = dC[p] * w;
@@ -910,25 +930,26 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
                     ctop = 2. * FLEX_PI * FLEX_GC * (fc.A * fc.rcf);
                     bool bad = false;
                     for (int s = 0; s < a.ns; s++) {
-                        if (shared_zc) {
-                            sdeep[s * FIT_NT + tid] = (fc.wd == 0.) ? 1. : exp(-a.k[s] * fc.wd);
+                        if (DRY) {
+                        } else if (shared_zc) {
+                            sdeep[s * LNT + tid] = (fc.wd == 0.) ? 1. : exp(-a.k[s] * fc.wd);
                         } else {
                             const FlexK q = flex_k(fc, a.k[s]);
-                            sdeep[s * FIT_NT + tid] = q.deep;
-                            if (two) stop[s * FIT_NT + tid] = q.top;
+                            sdeep[s * LNT + tid] = q.deep;
+                            if (two) stop[s * LNT + tid] = q.top;
                         }
                         const size_t o = src + nxy * s;
                         if (use_adm) {
                             const double y = __ldg(a.adm + o), e = __ldg(a.eadm + o);
                             bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
-                            sobs[(0 * a.ns + s) * FIT_NT + tid] = y;
-                            sobs[(1 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                            sobs[(0 * a.ns + s) * LNT + tid] = y;
+                            sobs[(1 * a.ns + s) * LNT + tid] = rcp_nr(e);
                         }
                         if (use_coh) {
                             const double y = __ldg(a.coh + o), e = __ldg(a.ecoh + o);
                             bad = bad || !isfinite(y) || !isfinite(e) || e == 0.;
-                            sobs[(2 * a.ns + s) * FIT_NT + tid] = y;
-                            sobs[(3 * a.ns + s) * FIT_NT + tid] = rcp_nr(e);
+                            sobs[(2 * a.ns + s) * LNT + tid] = y;
+                            sobs[(3 * a.ns + s) * LNT + tid] = rcp_nr(e);
                         }
                     }
                     if (bad) {  // SciPy raises ValueError here; we flag the cell
@@ -1072,6 +1093,19 @@ __global__ void __launch_bounds__(FIT_NT, 2) fit_lane_kernel(FitArgs a)
             }
         }
     }
+}
+
+// dry-land flag of a launch (see fit_lane_kernel<NP, DRY>): starts at 1, cleared by any fitted cell under water
+__global__ void wet_kernel(FitArgs a, int *flag)
+{
+    const long long ncells = (long long)a.fx * a.fy;
+    bool wet = false;
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncells; cell += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(cell % a.fx), cj = (int)(cell / a.fx);
+        const size_t src = (size_t)((a.cj0 + cj) * a.nn - a.row0) * a.nx + (size_t)ci * a.nn;
+        wet = wet || !(a.wd[src] == 0.);
+    }
+    if (wet) *flag = 0;
 }
 
 // ---- the fit kernel ---------------------------------------------------------------
@@ -1253,6 +1287,8 @@ int launch_fit_np(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
     return PFX_OK;
 }
 
+void launch_wet_kernel(const FitArgs &a, int *flag, int blocks, cudaStream_t st) { wet_kernel<<<blocks, 256, 0, st>>>(a, flag); }
+
 int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
 {
     const long long ncells = (long long)a.fx * a.fy;
@@ -1275,9 +1311,20 @@ int launch_fit_cell(const FitArgs &a, int alph, cudaStream_t stream, int nsm)
     const char *me = getenv("PLATEFLEX_B200_FIT");
     const bool lanes = cache && a.counter && !(me && !strcmp(me, "static"));
     if (lanes) {
-        const int resident = 2 * nsm;  // two CTAs per SM, each lane pulls cells until the counter runs out
-        if (blocks > resident) blocks = resident;
-        PFX_CHECK(alph ? launch(fit_lane_kernel<3>) : launch(fit_lane_kernel<2>));
+        // two CTAs per SM, each lane pulls cells until the counter runs out; the dry-land form (five CTAs of 64
+        // lanes, no depth array) is launched next to it and the device flag decides which of the two works
+        const size_t smem_dry = (2 * (size_t)a.ns + 4 * (size_t)a.ns * FIT_NT_DRY) * sizeof(double);
+        const long long wet_blocks = std::min<long long>((ncells + FIT_NT - 1) / FIT_NT, 2LL * nsm);
+        const long long dry_blocks = std::min<long long>((ncells + FIT_NT_DRY - 1) / FIT_NT_DRY, (long long)FIT_CTAS_DRY * nsm);
+        auto launch2 = [&](auto wet, auto dry) -> int {
+            PFX_CUDA(cudaFuncSetAttribute(wet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PFX_CUDA(cudaFuncSetAttribute(dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dry));
+            wet<<<(unsigned)wet_blocks, FIT_NT, smem, stream>>>(a);
+            dry<<<(unsigned)dry_blocks, FIT_NT_DRY, smem_dry, stream>>>(a);
+            return PFX_OK;
+        };
+        PFX_CHECK(alph ? launch2(fit_lane_kernel<3, false>, fit_lane_kernel<3, true>)
+                       : launch2(fit_lane_kernel<2, false>, fit_lane_kernel<2, true>));
     } else if (alph) {
         PFX_CHECK(cache ? launch(fit_cell_kernel<3, true>) : launch(fit_cell_kernel<3, false>));
     } else {
@@ -1298,7 +1345,7 @@ using namespace pfx;
 // concurrent fits on different streams cannot touch each other's counters.
 namespace {
 struct FitScratch {
-    unsigned long long *words = nullptr;  // [0] work counter, [1] todo count
+    unsigned long long *words = nullptr;  // [0] work counter, [1] todo count, [2] dry-land flag (as int), [3] unused
     int *todo = nullptr;
     int todo_cap = 0;
 };
@@ -1309,7 +1356,7 @@ int fit_scratch_alloc(FitScratch &sc, long long ncells, cudaStream_t st)
     if (cap > ncells) cap = ncells;
     if (cap < 1) cap = 1;
     void *p = nullptr;
-    const size_t bytes = 16 + (size_t)cap * sizeof(int);
+    const size_t bytes = 32 + (size_t)cap * sizeof(int);
     cudaError_t e = cudaMallocAsync(&p, bytes, st);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1317,9 +1364,9 @@ int fit_scratch_alloc(FitScratch &sc, long long ncells, cudaStream_t st)
         return e == cudaErrorMemoryAllocation ? PFX_ERR_OOM : PFX_ERR_CUDA;
     }
     sc.words = static_cast<unsigned long long *>(p);
-    sc.todo = reinterpret_cast<int *>(sc.words + 2);
+    sc.todo = reinterpret_cast<int *>(sc.words + 4);
     sc.todo_cap = (int)cap;
-    PFX_CUDA(cudaMemsetAsync(sc.words, 0, 16, st));
+    PFX_CUDA(cudaMemsetAsync(sc.words, 0, 32, st));
     return PFX_OK;
 }
 }  // namespace
@@ -1435,6 +1482,18 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
         rc = fit_scratch_alloc(scratch, (long long)a.fx * a.fy, st);
         if (rc == PFX_OK) {
             a.counter = scratch.words;
+            // dry-land form of the lane kernel: one crustal thickness and no fitted cell under water
+            // (PLATEFLEX_B200_FIT_DRY=off: always the general form)
+            int *flag = reinterpret_cast<int *>(scratch.words + 2);
+            a.dry_flag = flag;
+            const char *de = getenv("PLATEFLEX_B200_FIT_DRY");
+            if (!zc_map && !(de && !strcmp(de, "off"))) {
+                PFX_CUDA(cudaMemsetAsync(flag, 1, 1, st));  // little-endian int 1
+                int nsm_ = 148;
+                cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, device);
+                pfx::launch_wet_kernel(a, flag, nsm_ * 4, st);
+                PFX_CUDA(cudaGetLastError());
+            }
             // PLATEFLEX_B200_FIT_CAP: model evaluations after which a lane hands its cell to the finisher (0: never)
             const char *ce = getenv("PLATEFLEX_B200_FIT_CAP");
             const int capv = ce ? atoi(ce) : 32;

@@ -50,6 +50,7 @@ struct pfx_plan {
     double2 *d_spec[2] = {nullptr, nullptr};
     bool spec_t = false;
     double *d_partial = nullptr;  // deterministic two-stage sum for the mean
+    int *d_flag_words = nullptr;  // [2] flag words of the reduction, one per coefficient-plane buffer
     cufftHandle fft_fwd = 0;
     bool fft_fwd_ok = false;
 

@@ -32,6 +32,9 @@ using prn::csub;
 
 constexpr int NT = 128;
 constexpr int LOGCH = 11;  // 16 elements per thread
+#ifndef PFX_V4_MULTI_OCC
+#define PFX_V4_MULTI_OCC 3  // CTAs per SM the several-parts-per-line kernels are compiled for (168 registers)
+#endif
 
 // radix plan: first stage 16, then one stage (L <= 256) or radix 8 followed by the rest (L <= 2048)
 __host__ __device__ constexpr int nstages(int logl) { return logl - 4 <= 4 ? 2 : 3; }
@@ -357,7 +360,7 @@ struct Pass2Group {
 };
 
 template <int LOGL, bool MULTI>
-__global__ void __launch_bounds__(NT, MULTI ? 3 : 4) pass2_kernel(V4Args a)
+__global__ void __launch_bounds__(NT, MULTI ? PFX_V4_MULTI_OCC : 4) pass2_kernel(V4Args a)
 {
     using G = Geo<LOGL>;
     extern __shared__ double2 smem[];

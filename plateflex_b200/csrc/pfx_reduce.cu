@@ -77,28 +77,19 @@ __device__ __forceinline__ double jk_sgram(const double (&s)[NA])
 // (ad = xp*p2/(p1*p2)) with one fused multiply-add each; the sums are non-negative, so "a sum is 0" is "the
 // product is 0", read from its exponent and mantissa bits with integer instructions; results differ from the
 // reference's IEEE divisions by a few ulp, far inside the 1e-9 parity budget, at well under half of the FP64 work.
-// Otherwise (grids of extreme amplitude, exact zeros): the reference's own guard (p1 /= 0 .and. p2 /= 0) and IEEE divisions,
-// formed as (xp/p1)*(xp/p2) so that the product of the two sums is never taken.
-template <bool FAST>
+// Otherwise (grids of extreme amplitude, exact zeros): jk_admit_coh_exact below.
 __device__ __forceinline__ void ratio_acc(double q1, double q2, double qx, double &sa, double &sc)
 {
-    if (FAST) {
-        const double prod = q1 * q2;
-        const double xr = qx * fast_rcp(prod);
-        const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
-        const double f = ok ? xr : 0.0;
-        sc = fma(qx, f, sc);
-        sa = fma(q2, f, sa);
-    } else if (q1 != 0.0 && q2 != 0.0) {
-        const double ad = qx / q1;
-        sa += ad;
-        sc += ad * (qx / q2);
-    }
+    const double prod = q1 * q2;
+    const double xr = qx * fast_rcp(prod);
+    const bool ok = ((__double2hiint(prod) & 0x7fffffff) | __double2loint(prod)) != 0;
+    const double f = ok ? xr : 0.0;
+    sc = fma(qx, f, sc);
+    sa = fma(q2, f, sa);
 }
 
 // cpwt_sub.f90:298-366, same shared-prefix walk: 10 + 55 ratio evaluations
 // instead of the reference's 110.
-template <bool FAST>
 __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const double (&s2)[NA], const double (&xr)[NA],
                                              double &ead, double &eco)
 {
@@ -112,7 +103,7 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             q1 += s1[a2];
             q2 += s2[a2];
             qx += xr[a2];
-            ratio_acc<FAST>(q1, q2, qx, sa, sc);
+            ratio_acc(q1, q2, qx, sa, sc);
         }
         ad2[a] = sa * (1.0 / (double)(NA - 1));
         co2[a] = sc * (1.0 / (double)(NA - 1));
@@ -120,20 +111,11 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             p1 += s1[a];
             p2 += s2[a];
             px += xr[a];
-            ratio_acc<FAST>(p1, p2, px, cad, cco);
+            ratio_acc(p1, p2, px, cad, cco);
         }
     }
     ead = jk_spread(ad2);
     eco = jk_spread(co2);
-}
-
-// The rare path, out of line so that it costs the common one neither registers nor instruction cache.
-struct JkTriples {
-    double s1[NA], s2[NA], xr[NA];
-};
-__device__ __noinline__ void jk_admit_coh_exact(const JkTriples t, double *ead, double *eco)
-{
-    jk_admit_coh<false>(t.s1, t.s2, t.xr, *ead, *eco);
 }
 
 // High words of the doubles 1e-150 and 1e150: a power whose high word lies in [LO, HI] is a normal number in
@@ -153,6 +135,37 @@ __device__ __forceinline__ double2 load_w(const PlaneView &v, int p, int i, int 
     return make_double2(w.x * v.scale, w.y * v.scale);
 }
 
+// The rare path of the admittance / coherence jackknife (cells with a power outside [1e-150, 1e150], see
+// reduce_kernel and fixup_kernel): cpwt_sub.f90:310-357 literally -- eleven walks of ten running sums, the
+// reference's guard, IEEE divisions, the coherence quotient formed as (xp/p1)*(xp/p2) so that p1*p2 is never taken
+// -- as rolled loops that read the coefficients again.
+__device__ __forceinline__ void jk_admit_coh_exact(const PlaneView &w1, const PlaneView &w2, int i, int j, double2 zz, double &ead,
+                                   double &eco)
+{
+    double ad2[NA], co2[NA];
+#pragma unroll 1
+    for (int a = 0; a < NA; a++) {
+        double p1 = 0.0, p2 = 0.0, px = 0.0, sa = 0.0, sc = 0.0;
+#pragma unroll 1
+        for (int a2 = 0; a2 < NA; a2++) {
+            if (a2 == a) continue;
+            const double2 u = load_w(w1, a2, i, j, zz), v = load_w(w2, a2, i, j, zz);
+            p1 += fabs(u.x * u.x + u.y * u.y);
+            p2 += fabs(v.x * v.x + v.y * v.y);
+            px += u.x * v.x + u.y * v.y;
+            if (p1 != 0.0 && p2 != 0.0) {
+                const double ad = px / p1;
+                sa += ad;
+                sc += ad * (px / p2);
+            }
+        }
+        ad2[a] = sa * (1.0 / (double)(NA - 1));
+        co2[a] = sc * (1.0 / (double)(NA - 1));
+    }
+    ead = jk_spread(ad2);
+    eco = jk_spread(co2);
+}
+
 // F32: the outputs are float arrays (same element offsets): each float64 result is rounded once on store.
 template <bool F32>
 __device__ __forceinline__ void put(double *base, size_t o, double v)
@@ -163,25 +176,42 @@ __device__ __forceinline__ void put(double *base, size_t o, double v)
         base[o] = v;
 }
 
+// the four maps of the shard that owns row j: [map][scale][row in shard][x]
+__device__ __forceinline__ void shard_dest(const ShardOut &sh, int nx, int ny, int i, int j, double *&out0, double *&out1,
+                                           double *&out2, double *&out3, size_t &o)
+{
+    const int q = j / sh.rows_per_shard, jl = j - q * sh.rows_per_shard;
+    const int rq = min(sh.rows_per_shard, ny - q * sh.rows_per_shard);
+    const size_t map_stride = (size_t)sh.ns * rq * nx;
+    out0 = sh.base[q];
+    out1 = out0 + map_stride;
+    out2 = out1 + map_stride;
+    out3 = out2 + map_stride;
+    o = ((size_t)sh.scale * rq + jl) * nx + i;
+}
+
+// smallest high word of the 22 powers and the check itself (see reduce_kernel)
+__device__ __forceinline__ bool powers_out_of_range(int hmin, double t1sum, double t2sum)
+{
+    return hmin < PW_HI_LO || max(__double2hiint(t1sum), __double2hiint(t2sum)) > PW_HI_HI;
+}
+
 template <int MODE, bool SHARDED, bool F32, int OCC = 4>
 __global__ void __launch_bounds__(128, OCC)
     reduce_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out0, double *__restrict__ out1,
-                  double *__restrict__ out2, double *__restrict__ out3, ShardOut sh)
+                  double *__restrict__ out2, double *__restrict__ out3, ShardOut sh, int *odd_flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= nx) return;
     size_t o = (size_t)j * nx + i;
     if (SHARDED) {
-        // the four maps of the shard that owns row j: [map][scale][row in shard][x]
-        const int q = j / sh.rows_per_shard, jl = j - q * sh.rows_per_shard;
-        const int rq = min(sh.rows_per_shard, ny - q * sh.rows_per_shard);
-        const size_t map_stride = (size_t)sh.ns * rq * nx;
-        out0 = sh.base[q];
-        out1 = out0 + map_stride;
-        out2 = out1 + map_stride;
-        out3 = out2 + map_stride;
-        o = ((size_t)sh.scale * rq + jl) * nx + i;
+        double *p0, *p1, *p2, *p3;
+        shard_dest(sh, nx, ny, i, j, p0, p1, p2, p3, o);
+        out0 = p0;
+        out1 = p1;
+        out2 = p2;
+        out3 = p3;
     }
     const double2 z1 = load_z(w1, i, j);  // both grids' terms live in one array
     const double2 z2 = z1;
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(128, OCC)
     } else {
         double s1[NA], s2[NA], xr[NA];
         double t1 = 0.0, t2 = 0.0, tx = 0.0;
-        int hmin = 0x7fffffff, hmax = 0;  // range of the high words of the 22 powers (non-negative doubles)
+        int hmin = 0x7fffffff;  // smallest high word of the 22 powers (non-negative doubles)
 #pragma unroll
         for (int a = 0; a < NA; a++) {
             const double2 u = load_w(w1, a, i, j, z1), v = load_w(w2, a, i, j, z2);
@@ -223,17 +253,16 @@ __global__ void __launch_bounds__(128, OCC)
             xr[a] = u.x * v.x + u.y * v.y;        // Re(w1*CONJG(w2)), cpwt.f90:335
 #ifndef PFX_RED_NOCHECK
             hmin = min(hmin, min(__double2hiint(s1[a]), __double2hiint(s2[a])));
-            hmax = max(hmax, max(__double2hiint(s1[a]), __double2hiint(s2[a])));
 #endif
             t1 += s1[a];
             t2 += s2[a];
             tx += xr[a];
         }
-        // a power that is zero, subnormal, beyond [1e-150, 1e150] or not finite: the cell takes the exact path
+        // a power that is zero, subnormal or below 1e-150, or a sum over azimuths beyond 1e150 / not finite (every
+        // prefix sum lies between the smallest power and that sum): the cell takes the exact path
+        // -- flagged for fixup_kernel, which recomputes its two error values after this kernel
 #ifndef PFX_RED_NOCHECK
-        const bool odd = hmin < PW_HI_LO || hmax > PW_HI_HI;
-#else
-        const bool odd = false;
+        if (powers_out_of_range(hmin, t1, t2)) *odd_flag = 1;
 #endif
         t1 = t1 * (1.0 / (double)NA);  // cpwt.f90:348-350
         t2 = t2 * (1.0 / (double)NA);
@@ -241,18 +270,41 @@ __global__ void __launch_bounds__(128, OCC)
         put<F32>(out0, o, tx / t1);                                            // cpwt.f90:354
         put<F32>(out2, o, (tx * tx) / (t1 * t2));                              // cpwt.f90:355
         double ead, eco;
-        if (odd) {
-            JkTriples t;
-#pragma unroll
-            for (int a = 0; a < NA; a++) {
-                t.s1[a] = s1[a];
-                t.s2[a] = s2[a];
-                t.xr[a] = xr[a];
-            }
-            jk_admit_coh_exact(t, &ead, &eco);
-        } else {
-            jk_admit_coh<true>(s1, s2, xr, ead, eco);
+        jk_admit_coh(s1, s2, xr, ead, eco);
+        put<F32>(out1, o, ead);
+        put<F32>(out3, o, eco);
+    }
+}
+
+// Second half of the admittance / coherence epilogue: when reduce_kernel met a cell whose powers leave
+// [1e-150, 1e150] (odd_flag), every such cell gets its two jackknife errors from the exact path.  A small persistent
+// grid that returns at once in the common case.
+template <bool SHARDED, bool F32>
+__global__ void __launch_bounds__(128)
+    fixup_kernel(int nx, int ny, PlaneView w1, PlaneView w2, double *__restrict__ out1g, double *__restrict__ out3g,
+                 ShardOut sh, const int *odd_flag)
+{
+    if (*odd_flag == 0) return;
+    const size_t ncell = (size_t)nx * ny;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(c % nx), j = (int)(c / nx);
+        const double2 zz = load_z(w1, i, j);
+        int hmin = 0x7fffffff;
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll 1
+        for (int a = 0; a < NA; a++) {
+            const double2 u = load_w(w1, a, i, j, zz), v = load_w(w2, a, i, j, zz);
+            const double p1 = fabs(u.x * u.x + u.y * u.y), p2 = fabs(v.x * v.x + v.y * v.y);
+            hmin = min(hmin, min(__double2hiint(p1), __double2hiint(p2)));
+            t1 += p1;
+            t2 += p2;
         }
+        if (!powers_out_of_range(hmin, t1, t2)) continue;
+        double *out0 = nullptr, *out1 = out1g, *out2 = nullptr, *out3 = out3g;
+        size_t o = c;
+        if (SHARDED) shard_dest(sh, nx, ny, i, j, out0, out1, out2, out3, o);
+        double ead, eco;
+        jk_admit_coh_exact(w1, w2, i, j, zz, ead, eco);
         put<F32>(out1, o, ead);
         put<F32>(out3, o, eco);
     }
@@ -276,7 +328,7 @@ __global__ void crop_kernel(int nx, int ny, PlaneView w, void *__restrict__ slab
 }  // namespace
 
 int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *out0, double *out1, double *out2,
-                  double *out3, cudaStream_t stream, const ShardOut *shards, bool f32)
+                  double *out3, cudaStream_t stream, const ShardOut *shards, bool f32, int *flag_word)
 {
     dim3 block(128), grid((nx + 127) / 128, ny);
     const ShardOut none;
@@ -284,36 +336,46 @@ int launch_reduce(int mode, int nx, int ny, PlaneView w1, PlaneView w2, double *
         const char *e = getenv("PLATEFLEX_B200_REDUCE_OCC");
         return (e && e[0] == '3') ? 3 : 4;
     }();
-    if (shards && shards->nshards > 0) {
-        PFX_ARG(mode == RED_ADMIT_COH && !f32, "row-sharded output exists for the float64 admittance / coherence epilogue only");
-        if (occ == 3)
-            reduce_kernel<RED_ADMIT_COH, true, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
-                                                                                  nullptr, *shards);
-        else
-            reduce_kernel<RED_ADMIT_COH, true, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr,
-                                                                               nullptr, *shards);
-        PFX_CUDA(cudaGetLastError());
-        return PFX_OK;
-    }
+    const bool sharded = shards && shards->nshards > 0;
+    if (sharded) PFX_ARG(mode == RED_ADMIT_COH && !f32, "row-sharded output exists for the float64 admittance / coherence epilogue only");
     PFX_ARG(!(f32 && mode == RED_XSCALOGRAM), "float32 outputs exist for the scalogram and admittance / coherence epilogues");
     switch (mode) {
         case RED_SCALOGRAM:
             if (f32)
-                reduce_kernel<RED_SCALOGRAM, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+                reduce_kernel<RED_SCALOGRAM, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, nullptr);
             else
-                reduce_kernel<RED_SCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+                reduce_kernel<RED_SCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, nullptr);
             break;
         case RED_XSCALOGRAM:
-            reduce_kernel<RED_XSCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+            reduce_kernel<RED_XSCALOGRAM, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, nullptr);
             break;
-        case RED_ADMIT_COH:
-            if (f32)
-                reduce_kernel<RED_ADMIT_COH, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
-            else if (occ == 3)
-                reduce_kernel<RED_ADMIT_COH, false, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
-            else
-                reduce_kernel<RED_ADMIT_COH, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none);
+        case RED_ADMIT_COH: {
+            // per-launch flag word, allocated and freed in stream order: "some cell needs the exact jackknife"
+            int *flag = flag_word;
+            if (!flag_word) PFX_CUDA(cudaMallocAsync((void **)&flag, sizeof(int), stream));
+            PFX_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+            const ShardOut &sh = sharded ? *shards : none;
+            const dim3 fgrid(148 * 4);  // a small persistent grid (any size is correct)
+            if (sharded) {
+                if (occ == 3)
+                    reduce_kernel<RED_ADMIT_COH, true, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr, nullptr, sh, flag);
+                else
+                    reduce_kernel<RED_ADMIT_COH, true, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, nullptr, nullptr, sh, flag);
+                fixup_kernel<true, false><<<fgrid, block, 0, stream>>>(nx, ny, w1, w2, nullptr, nullptr, sh, flag);
+            } else if (f32) {
+                reduce_kernel<RED_ADMIT_COH, false, true><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, flag);
+                fixup_kernel<false, true><<<fgrid, block, 0, stream>>>(nx, ny, w1, w2, out1, out3, none, flag);
+            } else {
+                if (occ == 3)
+                    reduce_kernel<RED_ADMIT_COH, false, false, 3><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, flag);
+                else
+                    reduce_kernel<RED_ADMIT_COH, false, false><<<grid, block, 0, stream>>>(nx, ny, w1, w2, out0, out1, out2, out3, none, flag);
+                fixup_kernel<false, false><<<fgrid, block, 0, stream>>>(nx, ny, w1, w2, out1, out3, none, flag);
+            }
+            PFX_CUDA(cudaGetLastError());
+            if (!flag_word) PFX_CUDA(cudaFreeAsync(flag, stream));
             break;
+        }
         default:
             set_error("launch_reduce: bad mode %d", mode);
             return PFX_ERR_ARG;
