@@ -206,10 +206,21 @@ def _compare_fit(got_mean, got_std, got_chi2, ref_mean, ref_std, ref_chi2, npar)
     if on_bound:
         return False
     tol = [TE_TOL, F_TOL, A_TOL][:npar]
+    # Interior optimum.  Where a parameter is poorly determined (its standard deviation many times the tolerance:
+    # a flat valley of chi2, typical of Te at low coherence) two optimisers that both stop within ftol = 1e-8 stop
+    # at different points of the valley -- chi2 agrees (checked above to 1e-4), the parameter only to a fraction
+    # of its own uncertainty: |d| < max(tolerance, 0.2 sigma), sigma the larger of the two optimisers' standard
+    # deviations (they vary along the valley).  Standard deviations are compared where the
+    # parameters themselves agree to the tolerance (they are evaluated at the optimum and vary along the valley).
+    sharp = True
     for j in range(npar):
-        assert abs(got_mean[j] - ref_mean[j]) < tol[j], (j, got_mean, ref_mean)
-        assert got_std[j] == pytest.approx(ref_std[j], rel=STD_RTOL), (j, got_std, ref_std)
-    return True
+        d = abs(got_mean[j] - ref_mean[j])
+        assert d < max(tol[j], 0.2 * max(ref_std[j], got_std[j])), (j, got_mean, ref_mean, ref_std, got_std)
+        sharp = sharp and d < tol[j]
+    if sharp:
+        for j in range(npar):
+            assert got_std[j] == pytest.approx(ref_std[j], rel=STD_RTOL), (j, got_std, ref_std)
+    return sharp
 
 
 @pytest.mark.parametrize("atype", ["joint", "admit", "coh"])
@@ -940,5 +951,6 @@ def test_f2py_helper_exports_match_oracle(pf, ora):
     assert np.allclose(kx, rkx, rtol=1e-15) and np.allclose(ky, rky, rtol=1e-15) and kx[8] > 0
     w = cpwt.wave_function(kx, ky, pf.cf_wt.k0, 30.0, 0.4)
     rw = ora.wave_function(kx, ky, pf.cf_wt.k0, 30.0, 0.4)
-    assert w.shape == (16, 10) and np.allclose(w, rw, rtol=1e-12, atol=1e-300)
+    # (the DC element is an exact cancellation of the two Gaussians: compare it on the scale of the array)
+    assert w.shape == (16, 10) and np.allclose(w, rw, rtol=1e-12, atol=1e-15 * np.abs(rw).max())
     pf.set_conf_flex()
