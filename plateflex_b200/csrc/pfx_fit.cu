@@ -54,11 +54,10 @@ struct FitArgs {
     int32_t *status;
     unsigned long long *counter;  // lane-persistent kernel: next cell to hand out (zeroed before the launch)
     int fetch_min;                // ... lanes of a warp wait until this many of them need a new cell
-    // Tail control: once the work counter has run out, a lane gives up a cell that has not terminated after
-    // trial_cap model evaluations and appends it to todo[] (todo_count, zeroed before the launch; cells beyond
-    // todo_cap stay with their lane); the finisher -- the 8-lanes-per-cell kernel, a fraction of the latency per
-    // trial -- then fits exactly those cells from the start.  A cell that needs hundreds of trials no longer
-    // holds the whole grid for milliseconds at the end; while fresh cells remain nothing is handed over.
+    // Tail control: a lane gives up a cell that has not terminated after trial_cap model evaluations and appends it
+    // to todo[] (todo_count, zeroed before the launch; todo_cap = number of cells); the finisher -- the
+    // 8-lanes-per-cell kernel, a fraction of the latency per trial -- then fits exactly those cells from the start.
+    // A cell that needs hundreds of trials no longer holds the whole grid for milliseconds at the end.
     int *todo = nullptr;
     unsigned long long *todo_count = nullptr;
     int todo_cap = 0, trial_cap = 0;
@@ -980,14 +979,16 @@ __global__ void __launch_bounds__(DRY ? FIT_NT_DRY : FIT_NT, DRY ? FIT_CTAS_DRY 
             int status = -1;
             if (g_norm < TRF_GTOL) status = 1;
             bool handed_over = false;
-            // only in the tail: while fresh cells remain, a long cell costs nothing but its own lane
-            if (status == -1 && a.todo && nfev >= a.trial_cap && nfev < TRF_MAX_NFEV && ((nfev - a.trial_cap) & 7) == 0 &&
-                *reinterpret_cast<volatile unsigned long long *>(a.counter) >= (unsigned long long)ncells) {
+            // A cell that has not terminated after trial_cap model evaluations goes to the finisher -- always, whatever
+            // the state of the work counter, so that WHICH cells the finisher fits (its sums run in another order, the
+            // results differ in the last digits) depends on the cell alone: the maps are reproducible from run to run
+            // and identical between a row-sharded fit and the fit of the whole grid.  The list holds every cell.
+            if (status == -1 && a.todo && nfev == a.trial_cap) {
                 const unsigned long long slot = atomicAdd(a.todo_count, 1ull);
                 if (slot < (unsigned long long)a.todo_cap) {
                     a.todo[slot] = mycell;
                     handed_over = true;
-                }  // list full: the lane keeps the cell (the count is clamped by the finisher)
+                }
             }
             if (handed_over) {
                 have = false;
@@ -1352,8 +1353,7 @@ struct FitScratch {
 
 int fit_scratch_alloc(FitScratch &sc, long long ncells, cudaStream_t st)
 {
-    long long cap = ncells / 16 + 1024;  // cells that exceed the trial cap are well under 1 % of a grid
-    if (cap > ncells) cap = ncells;
+    long long cap = ncells;  // every cell may exceed the trial cap: the hand-over must never depend on a full list
     if (cap < 1) cap = 1;
     void *p = nullptr;
     const size_t bytes = 32 + (size_t)cap * sizeof(int);
@@ -1496,7 +1496,7 @@ int pfx_l2_fit_rows_dev(int device, void *stream, const pfx_flex_conf *conf, con
             }
             // PLATEFLEX_B200_FIT_CAP: model evaluations after which a lane hands its cell to the finisher (0: never)
             const char *ce = getenv("PLATEFLEX_B200_FIT_CAP");
-            const int capv = ce ? atoi(ce) : 32;
+            const int capv = ce ? atoi(ce) : (alph ? 0 : 64);  // the 3-parameter fit needs > 64 trials too often to pay
             if (capv > 0) {
                 a.todo = scratch.todo;
                 a.todo_count = scratch.words + 1;
