@@ -32,6 +32,10 @@ using prn::csub;
 
 constexpr int NT = 128;
 constexpr int LOGCH = 11;  // 16 elements per thread
+#ifndef PFX_V4_SPLIT_CHAIN
+#define PFX_V4_SPLIT_CHAIN 0
+#endif
+#define PFX_V4_HD __host__ __device__
 #ifndef PFX_V4_MULTI_OCC
 #define PFX_V4_MULTI_OCC 3  // CTAs per SM the several-parts-per-line kernels are compiled for (168 registers)
 #endif
@@ -209,6 +213,43 @@ __host__ __device__ __forceinline__ void dft16(double2 (&v)[16])
     }
 }
 
+// First-stage twiddles of one butterfly: t[k] = t0 g^k, times h from position w on (the support index wraps there;
+// w = lh when flag, lh + 1 otherwise, never 0).  Two independent chains (k < 8 from t0, k >= 8 from t0 g^8) halve
+// the depth of the dependent complex multiplies that every part starts with.
+PFX_V4_HD __forceinline__ void first_stage_twiddles(double2 t0, double2 g, double2 h, int lh, bool flag, double2 (&t)[16])
+{
+    const double2 one = make_double2(1., 0.);
+    const double2 ha = flag ? h : one, hb = flag ? one : h;
+#if PFX_V4_SPLIT_CHAIN
+    const int w = flag ? lh : lh + 1;
+    const double2 g8 = csqr(csqr(csqr(g)));
+    double2 a = t0, b = cmul(cmul(t0, g8), (w >= 1 && w <= 8) ? h : one);  // w = 0: input 0 already lies past the wrap
+    t[0] = a;
+    t[8] = b;
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        a = cmul(a, g);
+        b = cmul(b, g);
+        if (k == lh) a = cmul(a, ha);
+        if (k == lh + 1) a = cmul(a, hb);
+        if (k + 8 == lh) b = cmul(b, ha);
+        if (k + 8 == lh + 1) b = cmul(b, hb);
+        t[k] = a;
+        t[k + 8] = b;
+    }
+#else
+    double2 c = t0;
+    t[0] = c;
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        c = cmul(c, g);
+        if (k == lh) c = cmul(c, ha);
+        if (k == lh + 1) c = cmul(c, hb);
+        t[k] = c;
+    }
+#endif
+}
+
 // Stage S >= 1 of a part, in place; the last stage stores through store(q, rho, v).
 template <int LOGL, int S, bool HALF, class Store>
 __device__ __forceinline__ void stage(double2 *sm, const double2 *stw_all, const Store &store)
@@ -302,17 +343,10 @@ __device__ __forceinline__ void run_lines(double2 *sm, const double2 *stw, const
         for (int part = 0; part < (MULTI ? nparts : 1); part++) {
             // ---- first stage: twiddle the support samples, radix-16 butterfly into shared memory
             {
-                const double2 one = make_double2(1., 0.);
-                const double2 ha = flag ? h : one, hb = flag ? one : h;
-                double2 v[16];
-                double2 t = t0;
+                double2 v[16], tw[16];
+                first_stage_twiddles(t0, g, h, lh, flag, tw);
 #pragma unroll
                 for (int k = 0; k < 16; k++) {
-                    if (k > 0) {
-                        t = cmul(t, g);
-                        if (k == lh) t = cmul(t, ha);
-                        if (k == lh + 1) t = cmul(t, hb);
-                    }
                     double2 xin;
                     if (MULTI) {
                         xin = x[k];
@@ -320,7 +354,7 @@ __device__ __forceinline__ void run_lines(double2 *sm, const double2 *stw, const
                         const int m = (m0 + k * STEP) & (L - 1);
                         xin = (m < K) ? grp.load(gi, m) : make_double2(0., 0.);
                     }
-                    v[k] = cmul(xin, t);
+                    v[k] = cmul(xin, tw[k]);
                 }
                 dft16(v);
 #pragma unroll

@@ -94,19 +94,12 @@ static double run(int logN, int lo, int K, bool half)
             double2 t0 = root[(int)(((long long)a0 * (rg + 1)) & Nm)];
             const double2 g = root[((rg + 1) << G::LOGBF) & Nm];
             const double2 h = root[(N - (((rg + 1) << LOGL) & Nm)) & Nm];
-            const double2 one = make_double2(1., 0.);
-            const double2 ha = flag ? h : one, hb = flag ? one : h;
-            double2 v[16];
-            double2 t = t0;
+            double2 v[16], tw[16];
+            first_stage_twiddles(t0, g, h, lh, flag, tw);
             for (int k = 0; k < 16; k++) {
-                if (k > 0) {
-                    t = cmul(t, g);
-                    if (k == lh) t = cmul(t, ha);
-                    if (k == lh + 1) t = cmul(t, hb);
-                }
                 const int m = (m0 + k * STEP) & (L - 1);
                 const double2 xin = (m < K) ? x[m] : make_double2(0., 0.);
-                v[k] = cmul(xin, t);
+                v[k] = cmul(xin, tw[k]);
             }
             dft16(v);
             double2 *out0 = sm.data() + (padded<G::PAD>(u << 4) << G::LOGRC) + rho;
