@@ -90,11 +90,59 @@ __device__ __forceinline__ void ratio_acc(double q1, double q2, double qx, doubl
 
 // cpwt_sub.f90:298-366, same shared-prefix walk: 10 + 55 ratio evaluations
 // instead of the reference's 110.
+#ifndef PFX_RED_PAIR
+#define PFX_RED_PAIR 1
+#endif
 __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const double (&s2)[NA], const double (&xr)[NA],
                                              double &ead, double &eco)
 {
     double ad2[NA], co2[NA];
     double p1 = 0.0, p2 = 0.0, px = 0.0, cad = 0.0, cco = 0.0;
+#if PFX_RED_PAIR
+    // Walks a and a+1 side by side: from azimuth a+2 on both add the same powers, so their two dependent chains
+    // (sum, product, reciprocal, two fused multiply-adds) sit next to each other in program order and overlap in
+    // the FP64 pipe; every walk still adds in the reference's order, so the sums are those of the one-walk loop.
+#pragma unroll
+    for (int a = 0; a < NA; a += 2) {
+        double qa1 = p1, qa2 = p2, qax = px, saa = cad, sca = cco;  // walk a resumes from the prefix before a
+        if (a < NA - 1) {                                            // the shared prefix takes azimuth a
+            p1 += s1[a];
+            p2 += s2[a];
+            px += xr[a];
+            ratio_acc(p1, p2, px, cad, cco);
+        }
+        double qb1 = p1, qb2 = p2, qbx = px, sab = cad, scb = cco;  // walk a+1 resumes from the prefix before a+1
+        if (a + 1 < NA - 1) {                                        // ... and azimuth a+1
+            p1 += s1[a + 1];
+            p2 += s2[a + 1];
+            px += xr[a + 1];
+            ratio_acc(p1, p2, px, cad, cco);
+        }
+        if (a + 1 < NA) {  // walk a alone over azimuth a+1
+            qa1 += s1[a + 1];
+            qa2 += s2[a + 1];
+            qax += xr[a + 1];
+            ratio_acc(qa1, qa2, qax, saa, sca);
+        }
+#pragma unroll
+        for (int a2 = a + 2; a2 < NA; a2++) {
+            qa1 += s1[a2];
+            qb1 += s1[a2];
+            qa2 += s2[a2];
+            qb2 += s2[a2];
+            qax += xr[a2];
+            qbx += xr[a2];
+            ratio_acc(qa1, qa2, qax, saa, sca);
+            ratio_acc(qb1, qb2, qbx, sab, scb);
+        }
+        ad2[a] = saa * (1.0 / (double)(NA - 1));
+        co2[a] = sca * (1.0 / (double)(NA - 1));
+        if (a + 1 < NA) {
+            ad2[a + 1] = sab * (1.0 / (double)(NA - 1));
+            co2[a + 1] = scb * (1.0 / (double)(NA - 1));
+        }
+    }
+#else
 #pragma unroll
     for (int a = 0; a < NA; a++) {
         double q1 = p1, q2 = p2, qx = px, sa = cad, sc = cco;
@@ -114,6 +162,7 @@ __device__ __forceinline__ void jk_admit_coh(const double (&s1)[NA], const doubl
             ratio_acc(p1, p2, px, cad, cco);
         }
     }
+#endif
     ead = jk_spread(ad2);
     eco = jk_spread(co2);
 }
