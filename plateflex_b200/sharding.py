@@ -230,6 +230,77 @@ def gather_rows(local, nx_out, out_rows, group=None):
     return torch.cat(pieces)
 
 
+class _RawCuda:
+    """Zero-copy view of raw device memory for torch.as_tensor (the CUDA array interface, version 3)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def tensor_over(ptr, shape, dtype, device):
+    """torch tensor (no copy, no ownership) over device memory at ``ptr`` -- memory of pfx_ipc_alloc here."""
+    typestr = {torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_RawCuda(ptr, shape, typestr), device=device)
+
+
+class PeerResult:
+    """One-sided form of the result gather: rank ``dst`` owns an IPC-mappable buffer holding the (nmaps, my, mx)
+    float64 result maps followed by the (my, mx) int32 status words; every rank maps it and its fit kernel stores
+    the rows it fitted straight into place over NVLink.  No pack, no gather collective: a stream-ordered barrier
+    after the fits tells ``dst`` that everything has landed."""
+
+    def __init__(self, nmaps, my, mx, world, rank, device_index, dst=0, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._lib, self._C = _lib, C
+        self.nmaps, self.my, self.mx, self.rank, self.dst, self.device = nmaps, my, mx, rank, dst, device_index
+        self.world, self.group = world, group
+        self.map_bytes = my * mx * 8
+        nbytes = nmaps * self.map_bytes + my * mx * 4
+        self.own = None
+        handle = (C.c_ubyte * 64)()
+        if rank == dst:
+            self.own = C.c_void_p()
+            _lib.check(_lib.lib.pfx_ipc_alloc(device_index, max(nbytes, 16), C.byref(self.own), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = None
+        if rank == dst:
+            self.base = self.own.value
+        else:
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[dst])
+            _lib.check(_lib.lib.pfx_ipc_open(device_index, buf, C.byref(p)))
+            self.base, self._opened = p.value, p
+
+    def map_ptr(self, m, out_row0):
+        """Where this rank's first output row of map ``m`` lives in the owner's buffer."""
+        return self.base + m * self.map_bytes + out_row0 * self.mx * 8
+
+    def status_ptr(self, out_row0):
+        return self.base + self.nmaps * self.map_bytes + out_row0 * self.mx * 4
+
+    def tensors(self):
+        """On ``dst``: (nmaps, my, mx) float64 maps and (my, mx) int32 status, views of the owned buffer."""
+        dev = torch.device("cuda", self.device)
+        maps = tensor_over(self.base, (self.nmaps, self.my, self.mx), torch.float64, dev)
+        status = tensor_over(self.base + self.nmaps * self.map_bytes, (self.my, self.mx), torch.int32, dev)
+        return maps, status
+
+    def close(self):
+        if self.world > 1 and dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        if self._opened is not None:
+            self._lib.lib.pfx_ipc_close(self.device, self._opened)
+            self._opened = None
+        if self.own:
+            self._lib.lib.pfx_ipc_free(self.device, self.own)
+            self.own = None
+
+
 def stream_barrier(flag, group=None):
     """Stream-ordered barrier: a one-element all-reduce on the current stream.  Work enqueued after it on any
     rank starts only when every rank's stream has reached it -- without blocking the host, so a pipeline of
@@ -273,7 +344,7 @@ class TeMapPipeline:
     Everything is enqueued on the current CUDA stream of each rank; torch carries buffers and collectives."""
 
     def __init__(self, nx, ny, dx, dy, k, k0, conf, alph=False, atype="joint", nn=1, local_device=0, engine=None,
-                 group=None, balance="deal", solo=False):
+                 group=None, balance="deal", solo=False, gather=None):
         import ctypes as C
 
         import numpy as np
@@ -325,6 +396,16 @@ class TeMapPipeline:
         self.fit_out = torch.zeros((self.nmaps + 1) * mine, dtype=torch.float64, device=self.dev)
         self.fit_status = torch.zeros(mine, dtype=torch.int32, device=self.dev)
         self.mine = mine
+        # N > 1: the fit stores its maps straight into rank 0's result buffer (PeerResult); "nccl" keeps the
+        # packed gather collective (PLATEFLEX_B200_GATHER, or gather="nccl")
+        import os
+        self.result = None
+        if self.world > 1 and (gather or os.environ.get("PLATEFLEX_B200_GATHER", "p2p")) != "nccl":
+            self.result = PeerResult(self.nmaps, self.my, self.mx, self.world, self.rank, self.local, 0, group)
+            self.out_row0 = sum(self.out_rows[:self.rank])
+            if self.rank == 0:
+                self.res_maps, self.res_status = self.result.tensors()
+                self.res_all = torch.zeros((self.nmaps + 1, self.my, self.mx), dtype=torch.float64, device=self.dev)
 
     # ---- steps -------------------------------------------------------------------------------------
     def load(self, topo, grav, wd_f):
@@ -369,16 +450,30 @@ class TeMapPipeline:
         """Steps 4-5: fit of this rank's rows, gather on rank 0."""
         lib, C = self._lib.lib, self._C
         stream = self._bind_stream()
+        p2p = self.result is not None
         if self.nrows > 0 and self.out_rows[self.rank] > 0:
-            o = [self.fit_out.data_ptr() + i * self.mine * 8 for i in range(self.nmaps)]
+            if p2p:  # every output row at its place in rank 0's buffer
+                o = [self.result.map_ptr(i, self.out_row0) for i in range(self.nmaps)]
+                status_ptr = self.result.status_ptr(self.out_row0)
+            else:
+                o = [self.fit_out.data_ptr() + i * self.mine * 8 for i in range(self.nmaps)]
+                status_ptr = self.fit_status.data_ptr()
             te, te_s, f, f_s = o[0], o[1], o[2], o[3]
             al, al_s, chi2 = (o[4], o[5], o[6]) if self.alph else (None, None, o[4])
             wd = self.d_wd.data_ptr() + self.row0 * self.nx * 8
             self._lib.check(lib.pfx_l2_fit_rows_dev(
                 self.local, stream.cuda_stream, C.byref(self.conf), self.d_k.data_ptr(), self.ns, self.nx, self.ny,
                 self.row0, self.nrows, *self.map_ptrs, wd, None, None, None, self.nn, int(self.alph),
-                self._lib.ATYPES[self.atype], te, te_s, f, f_s, al, al_s, chi2, self.fit_status.data_ptr()))
-            self.fit_out[self.nmaps * self.mine:].copy_(self.fit_status)  # int32 -> float64, exact
+                self._lib.ATYPES[self.atype], te, te_s, f, f_s, al, al_s, chi2, status_ptr))
+            if not p2p:
+                self.fit_out[self.nmaps * self.mine:].copy_(self.fit_status)  # int32 -> float64, exact
+        if p2p:
+            stream_barrier(self.flag, self.group)  # every rank's rows have landed in rank 0's buffer
+            if self.rank != 0:
+                return None
+            self.res_all[:self.nmaps].copy_(self.res_maps)
+            self.res_all[self.nmaps].copy_(self.res_status)  # int32 -> float64, exact
+            return self.res_all
         if self.world > 1:
             return gather_rows_to_root(self.fit_out, self.nmaps + 1, self.mx, self.out_rows, 0, self.group)
         return self.fit_out.view(self.nmaps + 1, self.out_rows[0], self.mx)
@@ -387,6 +482,10 @@ class TeMapPipeline:
         return self.plan.launch_count()
 
     def close(self):
+        if getattr(self, "result", None) is not None:
+            self.res_maps = self.res_status = None
+            self.result.close()
+            self.result = None
         if self.peers is not None:
             self.peers.close()
             self.peers = None
