@@ -646,8 +646,9 @@ def main():
                    "cpu_affinity": f"{numa_cpus} CPUs of the GPU's NUMA node" if numa_cpus else "not set",
                    "balance": args.balance if sharded else None,
                    "sharding": ((f"scales over {world} ranks (dealt by cost), epilogue stores into peer row shards over "
-                                 f"NVLink (CUDA IPC), rows over {world} ranks for the fit; NCCL broadcast of the inputs "
-                                 "and gather of the maps inside the step") if sharded else
+                                 f"NVLink (CUDA IPC), rows over {world} ranks for the fit, whose kernel stores the result "
+                                 "maps into rank 0's buffer over NVLink; NCCL broadcast of the inputs and both "
+                                 "stream-ordered barriers inside the step") if sharded else
                                 (f"{world} independent grid pairs, one per rank" if world > 1 else "single GPU"))},
         "clocks": clocks.summary(),
         "e2e": r.get("e2e"), "gpu_launches": r["launches"],

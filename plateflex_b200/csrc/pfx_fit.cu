@@ -1357,6 +1357,23 @@ int fit_scratch_alloc(FitScratch &sc, long long ncells, cudaStream_t st)
     if (cap < 1) cap = 1;
     void *p = nullptr;
     const size_t bytes = 32 + (size_t)cap * sizeof(int);
+    {   // keep freed scratch in the device's pool across synchronisation points (the default threshold of 0 hands
+        // it back to the driver at every sync, and the next call pays milliseconds to map it again)
+        static std::mutex mu;
+        static bool done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev >= 0 && dev < 64 && !done[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            done[dev] = true;
+        }
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, st);
     if (e != cudaSuccess) {
         cudaGetLastError();
