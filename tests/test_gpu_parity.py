@@ -822,6 +822,33 @@ def _ipc_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_second_device_in_one_process_matches_the_first(pf, monkeypatch):
+    """One process, two devices: the host-pointer API on device 1 after device 0 has been used -- pageable host
+    copies above 4 MiB go through pinned staging chunks whose events belong to one device each (ADVICE r01:
+    a process-global staging area made any second device fail with an invalid resource handle)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from plateflex_b200 import _lib, estimate
+    from plateflex_b200.cpwt import fused
+    nx, ny, dx, dy = 600, 520, 5.0, 5.0  # 2.5 MB per scale and map: four scales make every copy exceed 4 MiB
+    t = red_field(nx, ny, seed=21) * 500.0
+    g = 0.08 * t + red_field(nx, ny, seed=22) * 20.0
+    kf = _wavenumbers(("ladder", 5), nx, ny, dx, dy)
+    outs = {}
+    for dev in ("0", "1"):
+        monkeypatch.setenv("PLATEFLEX_B200_DEVICE", dev)
+        _lib.clear_plans()
+        maps = fused.wlet_admit_coh(t, g, dx, dy, kf)
+        fit = estimate.L2_estimate_grid(kf, *maps, wd=np.zeros((nx, ny)), nn=8, alph=False, atype="joint")
+        outs[dev] = (maps, fit)
+    _lib.clear_plans()
+    for a, b in zip(outs["0"][0], outs["1"][0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    for name in ("mean_Te", "mean_F", "chi2", "status"):
+        assert np.array_equal(outs["0"][1][name], outs["1"][1][name], equal_nan=True), name
+
+
 def test_two_gpu_pipeline_equals_single_gpu_bit_for_bit(pf):
     """Two processes, two GPUs: scale-sharded transform with the epilogue storing into the peer's row shard
     through a CUDA-IPC mapping, stream-ordered barrier, row-sharded fit, gather -- the maps on rank 0 must be
