@@ -368,6 +368,7 @@ class TeMapPipeline:
         self.d_grav = torch.empty(nxy, dtype=torch.float64, device=self.dev)
         self.d_wd = torch.empty(nxy, dtype=torch.float64, device=self.dev)  # (nx, ny) x fastest: [j][i]
         self.nmaps = 7 if self.alph else 5
+        self._side, self._wd_event = None, None
         self.mx = self.nx // self.nn
         if self.world > 1:
             self.peers = PeerShards(nx, ny, self.ns, self.world, self.rank, self.local, group=group)
@@ -414,7 +415,14 @@ class TeMapPipeline:
         if self.rank == 0:
             self.d_topo.copy_(topo.reshape(-1), non_blocking=True)
             self.d_grav.copy_(grav.reshape(-1), non_blocking=True)
-            self.d_wd.copy_(wd_f.reshape(-1), non_blocking=True)
+            # the water depth is needed by the fit only: its copy runs on a side stream behind the transform
+            cur = torch.cuda.current_stream(self.dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.dev)
+            self._side.wait_stream(cur)  # the previous step's fit has read the old values
+            with torch.cuda.stream(self._side):
+                self.d_wd.copy_(wd_f.reshape(-1), non_blocking=True)
+            self._wd_event = self._side.record_event()
 
     def run(self):
         """One pass over the inputs currently in d_topo / d_grav / d_wd of rank 0; returns on rank 0 the
@@ -441,15 +449,22 @@ class TeMapPipeline:
         if self.world > 1:
             dist.broadcast(self.d_topo, 0, group=self.group)
             dist.broadcast(self.d_grav, 0, group=self.group)
-            dist.broadcast(self.d_wd, 0, group=self.group)
         self.run_cwt_only()
+        self._wait_wd()
         if self.world > 1:
+            dist.broadcast(self.d_wd, 0, group=self.group)  # needed by the fit only: behind the transform
             stream_barrier(self.flag, self.group)
+
+    def _wait_wd(self):
+        if self._wd_event is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self._wd_event)
+            self._wd_event = None
 
     def run_fit(self):
         """Steps 4-5: fit of this rank's rows, gather on rank 0."""
         lib, C = self._lib.lib, self._C
         stream = self._bind_stream()
+        self._wait_wd()
         p2p = self.result is not None
         if self.nrows > 0 and self.out_rows[self.rank] > 0:
             if p2p:  # every output row at its place in rank 0's buffer
