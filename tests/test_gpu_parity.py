@@ -822,6 +822,44 @@ def _ipc_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("nx,ny", [(44, 37), (16, 1024)])
+def test_cutoff_change_rebuilds_the_plan(pf, nx, ny):
+    """pfx_plan_set_cutoff re-plans the pruned engine (supports, FFT lengths, tables, the cosine-transform state on
+    power-of-two grids): 8.5 sigma instead of 9.5 changes the maps by less than the parity budget (the neglected
+    tail is e^{-36} of the peak), 5 sigma (e^{-12.5}) visibly -- so the new supports are really in use."""
+    import torch
+    from plateflex_b200 import _lib
+    dx = dy = 5.0
+    t = red_field(nx, ny, seed=31) * 500.0
+    g = 0.08 * t + red_field(nx, ny, seed=32) * 20.0
+    kf = _wavenumbers(("ladder", 3), nx, ny, dx, dy)
+    ns = len(kf)
+    dev = torch.device("cuda", 0)
+    d_t, d_g = torch.from_numpy(t).to(dev), torch.from_numpy(g).to(dev)
+    plan = _lib.Plan(nx, ny, dx, dy, kf, pf.cf_wt.k0, device=0)
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def run():
+        outs = [torch.empty(ns * nx * ny, dtype=torch.float64, device=dev) for _ in range(4)]
+        _lib.check(_lib.lib.pfx_wlet_admit_coh_dev(plan.handle, d_t.data_ptr(), d_g.data_ptr(), 0, ns, *[o.data_ptr() for o in outs]))
+        torch.cuda.synchronize()
+        return [o.cpu().numpy().reshape(ns, ny, nx) for o in outs]
+
+    ref = run()
+    plan.set_cutoff(8.5)
+    near = run()
+    plan.set_cutoff(5.0)
+    far = run()
+    plan.set_cutoff(9.5)
+    again = run()
+    plan.close()
+    for a, b, c, d in zip(ref, near, far, again):
+        mx = np.abs(a).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(a - b) / mx).max() < 1e-9
+        assert np.array_equal(a, d)
+    assert (np.abs(ref[0] - far[0]) / np.abs(ref[0]).max(axis=(1, 2), keepdims=True)).max() > 1e-9
+
+
 def test_second_device_in_one_process_matches_the_first(pf, monkeypatch):
     """One process, two devices: the host-pointer API on device 1 after device 0 has been used -- pageable host
     copies above 4 MiB go through pinned staging chunks whose events belong to one device each (ADVICE r01:
