@@ -99,6 +99,10 @@ int pfx_fp64_peak(int device, double *tflops);
 int pfx_dev_alloc(int device, size_t bytes, void **dev_ptr);
 int pfx_dev_free(int device, void *dev_ptr);
 int pfx_dev_h2d(int device, void *dst_dev, const void *src_host, size_t bytes);
+/* Upload of a C-order (rows, cols) host array of 8- or 1-byte elements as its Fortran-order image
+ * (dst[j*rows + i] = src[i*cols + j]): the (nx, ny) grids numpy hands over (water depth, rhoc, zc, mask --
+ * classes.py:1087-1091, 1228) reach the x-fastest layout of the maps without a strided copy on the host. */
+int pfx_dev_h2d_transposed(int device, void *dst_dev, const void *src_host, int rows, int cols, int elem_bytes);
 int pfx_dev_d2h(int device, void *dst_host, const void *src_dev, size_t bytes);
 
 /* ---- CWT plan --------------------------------------------------------- */

@@ -53,6 +53,7 @@ _SIGS = {
     "pfx_dev_alloc": ([_i, C.c_size_t, C.POINTER(_vp)], _i),
     "pfx_dev_free": ([_i, _vp], _i),
     "pfx_dev_h2d": ([_i, _vp, _vp, C.c_size_t], _i),
+    "pfx_dev_h2d_transposed": ([_i, _vp, _vp, _i, _i, _i], _i),
     "pfx_dev_d2h": ([_i, _vp, _vp, C.c_size_t], _i),
     "pfx_xyz_header": ([C.c_char_p, _vp], _i),
     "pfx_xyz_read": ([C.c_char_p, C.c_long, _vp, _i], _i),
@@ -161,6 +162,16 @@ class DeviceBuffer:
     def upload(self, arr):
         assert arr.nbytes <= self.nbytes and (arr.flags.c_contiguous or arr.flags.f_contiguous)
         check(lib.pfx_dev_h2d(self.device, C.c_void_p(self.ptr), ptr(arr), arr.nbytes))
+
+    @classmethod
+    def from_host_as_fortran(cls, arr, device=None):
+        """Device copy of a 2-D array in Fortran order (first index fastest) whatever its order on the host: a
+        C-ordered array is transposed on the GPU instead of through a strided numpy copy."""
+        if arr.ndim != 2 or arr.flags.f_contiguous or not arr.flags.c_contiguous or arr.itemsize not in (1, 8):
+            return cls.from_host(np.asfortranarray(arr), device)
+        buf = cls(arr.nbytes, device)
+        check(lib.pfx_dev_h2d_transposed(buf.device, C.c_void_p(buf.ptr), ptr(arr), arr.shape[0], arr.shape[1], arr.itemsize))
+        return buf
 
     def download(self, out, offset=0):
         assert offset + out.nbytes <= self.nbytes and (out.flags.c_contiguous or out.flags.f_contiguous)

@@ -128,6 +128,26 @@ cudaEvent_t pfx_plan::prof_event()
     return e;
 }
 
+namespace {
+// dst[j * rows + i] = src[i * cols + j]: the Fortran-order image of a C-order (rows, cols) array
+template <class T>
+__global__ void __launch_bounds__(256) transpose_kernel(int rows, int cols, const T *__restrict__ src, T *__restrict__ dst)
+{
+    __shared__ T tile[32][33];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + threadIdx.x;
+        if (i < rows && j < cols) tile[r][threadIdx.x] = src[(size_t)i * cols + j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += 8) {
+        const int i = i0 + threadIdx.x, j = j0 + c;
+        if (i < rows && j < cols) dst[(size_t)j * rows + i] = tile[threadIdx.x][c];
+    }
+}
+}  // namespace
+
+
 extern "C" {
 
 int pfx_version(void) { return 101; }
@@ -213,6 +233,31 @@ int pfx_dev_h2d(int device, void *dst_dev, const void *src_host, size_t bytes)
     PFX_CHECK(staged_h2d(dst_dev, src_host, bytes, 0));
     PFX_CUDA(cudaStreamSynchronize(0));
     return PFX_OK;
+}
+
+int pfx_dev_h2d_transposed(int device, void *dst_dev, const void *src_host, int rows, int cols, int elem_bytes)
+{
+    PFX_ARG(dst_dev && src_host, "null pointer");
+    PFX_ARG(rows >= 1 && cols >= 1 && (elem_bytes == 8 || elem_bytes == 1), "rows, cols >= 1 and 8- or 1-byte elements");
+    DeviceGuard guard(device);
+    const size_t bytes = (size_t)rows * cols * elem_bytes;
+    void *tmp = nullptr;
+    PFX_CUDA(cudaMalloc(&tmp, bytes));
+    int rc = staged_h2d(tmp, src_host, bytes, 0);
+    if (rc == PFX_OK) {
+        const dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+        if (elem_bytes == 8)
+            transpose_kernel<double><<<grid, block>>>(rows, cols, static_cast<const double *>(tmp), static_cast<double *>(dst_dev));
+        else
+            transpose_kernel<unsigned char><<<grid, block>>>(rows, cols, static_cast<const unsigned char *>(tmp),
+                                                             static_cast<unsigned char *>(dst_dev));
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(0) != cudaSuccess) {
+            set_error("transposing upload failed");
+            rc = PFX_ERR_CUDA;
+        }
+    }
+    cudaFree(tmp);
+    return rc;
 }
 
 int pfx_dev_d2h(int device, void *dst_host, const void *src_dev, size_t bytes)

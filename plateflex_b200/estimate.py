@@ -85,10 +85,10 @@ def L2_estimate_grid_device(k, dmaps, wd, rhoc=None, zc=None, mask=None, nn=1, a
     def up(a, name, dtype=np.float64):
         if a is None:
             return None
-        a = np.asfortranarray(a, dtype=dtype)
+        a = np.asarray(a, dtype=dtype)
         if a.shape != (nx, ny):
             raise ValueError(f"{name} must have shape ({nx}, {ny})")
-        return _lib.DeviceBuffer.from_host(a, dev)
+        return _lib.DeviceBuffer.from_host_as_fortran(a, dev)
 
     mx, my = nx // nn, ny // nn
     names = ["mean_Te", "std_Te", "mean_F", "std_F", "mean_a", "std_a", "chi2"]
