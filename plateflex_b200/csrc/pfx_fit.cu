@@ -103,13 +103,15 @@ __device__ void jacobi_eig(double (&A)[NP][NP], double (&lam)[NP], double (&V)[N
             for (int q = p + 1; q < NP; q++) {
                 const double apq = A[p][q];
                 if (apq == 0.) continue;
-                if (fabs(apq) <= DBL_EPS * 1e-3 * sqrt(fabs(A[p][p] * A[q][q]))) {
+                if (apq * apq <= (DBL_EPS * 1e-3) * (DBL_EPS * 1e-3) * fabs(A[p][p] * A[q][q])) {
                     A[p][q] = A[q][p] = 0.;  // negligible against the scaled diagonal
                     continue;
                 }
-                const double tau = (A[q][q] - A[p][p]) / (2. * apq);
-                const double t = (tau >= 0. ? 1. : -1.) / (fabs(tau) + sqrt(1. + tau * tau));
-                const double c = 1. / sqrt(1. + t * t), s = t * c;
+                // t = sgn(tau) / (|tau| + sqrt(1 + tau^2)), tau = h / (2 apq), h = Aqq - App, in one square root and
+                // one division:  t = 2 apq sgn(h) / (|h| + sqrt(h^2 + 4 apq^2))
+                const double h = A[q][q] - A[p][p], a2 = 2. * apq;
+                const double t = (h >= 0. ? a2 : -a2) / (fabs(h) + sqrt(h * h + a2 * a2));
+                const double c = rsqrt(1. + t * t), s = t * c;
                 A[p][p] -= t * apq;
                 A[q][q] += t * apq;
                 A[p][q] = A[q][p] = 0.;
@@ -232,10 +234,13 @@ template <int NP>
 __device__ void solve_tr(int m, const double (&lam)[NP], const double (&V)[NP][NP], const double (&suf)[NP],
                          double Delta, double &alpha, double (&p)[NP])
 {
-    double s[NP];
-#pragma unroll
-    for (int i = 0; i < NP; i++) s[i] = sqrt(fmax(lam[i], 0.));
-    const bool full_rank = (m >= NP) && (s[NP - 1] > DBL_EPS * m * s[0]);
+    // The optimiser's small algebra is a chain of dependent divisions and square roots executed by every lane of a
+    // warp at the pace of the slowest: they are kept to the minimum -- the rank test compares squares (the singular
+    // values are the square roots of lam), each secular-equation term takes one reciprocal instead of two
+    // quotients, and phi/phi' is formed directly.
+    const double lam0 = fmax(lam[0], 0.), lamn = fmax(lam[NP - 1], 0.);
+    const double rk = DBL_EPS * m;
+    const bool full_rank = (m >= NP) && (lamn > rk * rk * lam0);  // s[NP-1] > EPS * m * s[0]
     double w[NP];
     if (full_rank) {
 #pragma unroll
@@ -252,35 +257,36 @@ __device__ void solve_tr(int m, const double (&lam)[NP], const double (&V)[NP][N
             return;
         }
     }
-    auto phi_dphi = [&](double al, double &phi, double &dphi) {
+    // phi(al) = ||p(al)|| - Delta and ratio = phi / phi'  (phi' = -sum suf^2/(lam+al)^3 / ||p||)
+    auto phi_ratio = [&](double al, double &phi, double &ratio, double &pn) {
         double pn2 = 0., d3 = 0.;
 #pragma unroll
         for (int i = 0; i < NP; i++) {
-            const double den = lam[i] + al;
-            const double q = suf[i] / den;
+            const double r = 1. / (lam[i] + al);
+            const double q = suf[i] * r;
             pn2 += q * q;
-            d3 += suf[i] * suf[i] / (den * den * den);
+            d3 += (q * q) * r;
         }
-        const double pn = sqrt(pn2);
+        pn = sqrt(pn2);
         phi = pn - Delta;
-        dphi = -d3 / pn;
+        ratio = -(phi * pn) / d3;
     };
-    double alpha_upper = vnorm<NP>(suf) / Delta, alpha_lower = 0.;
+    const double inv_delta = 1. / Delta;
+    double alpha_upper = vnorm<NP>(suf) * inv_delta, alpha_lower = 0.;
     if (full_rank) {
-        double phi, dphi;
-        phi_dphi(0., phi, dphi);
-        alpha_lower = -phi / dphi;
+        double phi, ratio, pn;
+        phi_ratio(0., phi, ratio, pn);
+        alpha_lower = -ratio;
     }
     if (!full_rank && alpha == 0.) alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
     for (int it = 0; it < 10; it++) {
         if (alpha < alpha_lower || alpha > alpha_upper)
             alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
-        double phi, dphi;
-        phi_dphi(alpha, phi, dphi);
+        double phi, ratio, pn;
+        phi_ratio(alpha, phi, ratio, pn);
         if (phi < 0.) alpha_upper = alpha;
-        const double ratio = phi / dphi;
         alpha_lower = fmax(alpha_lower, alpha - ratio);
-        alpha -= (phi + Delta) * ratio / Delta;
+        alpha -= pn * ratio * inv_delta;  // (phi + Delta) * ratio / Delta
         if (fabs(phi) < 0.01 * Delta) break;
     }
 #pragma unroll
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(FIT_NT, CACHE ? 2 : FIT_MIN_BLOCKS) fit_cell_k
             const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
             double sa, ca;
             sincos(alpha, &sa, &ca);
-            const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+            const double te3 = te * te * te, rf = 1. / (1. - F), ff = F * rf, dff = rf * rf;
             double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
             for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
@@ -821,7 +827,7 @@ __global__ void __launch_bounds__(DRY ? FIT_NT_DRY : FIT_NT, DRY ? FIT_CTAS_DRY 
         const double al = (NP == 3) ? xe[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
         double sa, ca;
         sincos(al, &sa, &ca);
-        const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+        const double te3 = te * te * te, rf = 1. / (1. - F), ff = F * rf, dff = rf * rf;
         double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
         for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
@@ -1182,7 +1188,7 @@ __global__ void __launch_bounds__(128) fit_kernel(FitArgs a)
             const double alpha = (NP == 3) ? x[NP - 1] : FLEX_PI / 2.;  // estimate.py:292
             double sa, ca;
             sincos(alpha, &sa, &ca);
-            const double te3 = te * te * te, ff = F / (1. - F), dff = 1. / ((1. - F) * (1. - F));
+            const double te3 = te * te * te, rf = 1. / (1. - F), ff = F * rf, dff = rf * rf;
             double acc[1 + NP + NP * (NP + 1) / 2];
 #pragma unroll
             for (int q = 0; q < 1 + NP + NP * (NP + 1) / 2; q++) acc[q] = 0.;
